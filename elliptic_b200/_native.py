@@ -1,0 +1,84 @@
+"""ctypes binding of libelliptic_b200.so (the C ABI in include/elliptic_b200.h).
+
+There is deliberately no CPU fallback: if the shared library is missing or no
+CUDA device is usable, every compute call raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelliptic_b200.so")
+
+OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_NOT_INIT, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+ST_FALSE, ST_TRUE, ST_THROW_INVALID_POINT, ST_THROW_NOT_VALIDATED, ST_NEEDS_HOST, ST_THROW_ASSERT, \
+    ST_THROW_POINT_FORMAT = range(7)
+CURVE_SECP256K1, CURVE_P256, CURVE_P384, CURVE_ED25519, CURVE_CURVE25519 = 1, 2, 3, 4, 5
+PUB_XY, PUB_SEC1_65, PUB_SEC1_33 = 0, 1, 2
+
+EXPORTS = [
+    "eb200_init", "eb200_shutdown", "eb200_strerror", "eb200_last_error", "eb200_last_timing",
+    "eb200_ecdsa_verify_batch", "eb200_ecdsa_verify_workspace_bytes", "eb200_ecdsa_verify_batch_dev",
+    "eb200_selftest_fe", "eb200_selftest_gtab",
+]
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("h2d_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+                ("main_kernel_ms", ctypes.c_float), ("launches", ctypes.c_uint32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library (no CUDA call yet)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "libelliptic_b200.so is not built (run `python -m elliptic_b200.build`); "
+            "elliptic_b200 has no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    lib.eb200_init.argtypes = [c.c_int]
+    lib.eb200_strerror.restype = c.c_char_p
+    lib.eb200_strerror.argtypes = [c.c_int]
+    lib.eb200_last_error.restype = c.c_char_p
+    lib.eb200_last_timing.argtypes = [c.POINTER(Timing)]
+    lib.eb200_ecdsa_verify_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4 + [c.c_uint32, c.c_void_p]
+    lib.eb200_ecdsa_verify_workspace_bytes.restype = c.c_size_t
+    lib.eb200_ecdsa_verify_workspace_bytes.argtypes = [c.c_int, c.c_size_t]
+    lib.eb200_ecdsa_verify_batch_dev.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4 + [c.c_uint32] + [c.c_void_p] * 3
+    lib.eb200_selftest_fe.argtypes = [c.c_int, c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.eb200_selftest_gtab.argtypes = [c.c_int, c.c_void_p, c.c_size_t]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != OK:
+        lib = load()
+        raise NativeError("%s [%s]" % (lib.eb200_strerror(rc).decode(), lib.eb200_last_error().decode()))
+
+
+_inited = {}
+
+
+def init(device=0):
+    lib = load()
+    if _inited.get("dev") != device:
+        check(lib.eb200_init(device))
+        _inited["dev"] = device
+    return lib
+
+
+def last_timing():
+    t = Timing()
+    check(load().eb200_last_timing(ctypes.byref(t)))
+    return {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms,
+            "main_kernel_ms": t.main_kernel_ms, "launches": t.launches}

@@ -1,0 +1,206 @@
+// fe_k256.cuh -- arithmetic in GF(p), p = 2^256 - 2^32 - 977 (secp256k1).
+//
+// Replaces bn.js `Red` over the K256 pseudo-Mersenne prime for the hot path:
+//   Red.mul/sqr/add/sub/neg      reference dist/elliptic.js:7106-7175
+//   MPrime.ireduce + K256.split/imulK   dist/elliptic.js:6904-6934, 6952-7009
+// Design (B200-first, not a port of the 26-bit-limb JS code): 8 x 32-bit limbs
+// held in registers, "weakly reduced" values in [0, 2^256) (canonical form is
+// produced only where the reference exposes a residue: fe_normalize), products
+// folded with 2^256 = 2^32 + 977 (mod p).  One field multiplication is 64
+// IMAD.WIDE.U32 for the product + 9 for the fold; the add/sub chains run on
+// the ALU pipe in the shadow of the fma pipe.
+#pragma once
+#include "limbs.cuh"
+
+namespace eb {
+
+struct fe { u32 v[8]; };
+
+#define K256_C0 977u  // p = 2^256 - (2^32 + K256_C0)
+
+EB_HD fe fe_zero() { fe r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+EB_HD fe fe_one() { fe r = fe_zero(); r.v[0] = 1; return r; }
+
+// r += k * (2^32 + 977) over the full 8 limbs, k in {0,1}; returns carry out.
+EB_HD u32 fe_addc_k(u32* r, u32 k) {
+  u32 t[8] = {k ? K256_C0 : 0u, k, 0, 0, 0, 0, 0, 0};
+  return add_n<8>(r, r, t);
+}
+
+// Fold a 512-bit value t[16] to 8 limbs in [0, 2^256).
+EB_HD void fe_reduce512(u32* r, const u32* t) {
+  u32 A[10];
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {  // A = lo + hi*977   (9 limbs)
+    c += (u64)t[8 + j] * K256_C0 + t[j];
+    A[j] = (u32)c;
+    c >>= 32;
+  }
+  A[8] = (u32)c;
+  A[9] = add_n<8>(A + 1, A + 1, t + 8);  // += hi << 32
+  // second fold: top = A[8] + 2^32*A[9]  (< 2^33 + 2^11)
+  c = (u64)A[8] * K256_C0 + A[0];
+  r[0] = (u32)c; c >>= 32;
+  c += (u64)A[1] + A[8] + (A[9] ? K256_C0 : 0u);
+  r[1] = (u32)c; c >>= 32;
+  c += (u64)A[2] + A[9];
+  r[2] = (u32)c; c >>= 32;
+#pragma unroll
+  for (int j = 3; j < 8; j++) {
+    c += A[j];
+    r[j] = (u32)c; c >>= 32;
+  }
+  // c in {0,1}; if 1 the wrapped value is < 2^66 so adding 2^32+977 cannot carry past limb 2
+  u32 k = (u32)c;
+  c = (u64)r[0] + (k ? K256_C0 : 0u);
+  r[0] = (u32)c; c >>= 32;
+  c += (u64)r[1] + k;
+  r[1] = (u32)c; c >>= 32;
+  r[2] += (u32)c;
+}
+
+// Squaring.  v1: the general product (64 MACs); a dedicated 36-MAC version is
+// an optimisation candidate once the kernel is profiled.
+EB_HD void fe_sqr_wide(u32* r, const u32* a) { mul_wide<8>(r, a, a); }
+
+EB_HD fe fe_mul(const fe& a, const fe& b) {
+  u32 t[16];
+  mul_wide<8>(t, a.v, b.v);
+  fe r;
+  fe_reduce512(r.v, t);
+  return r;
+}
+
+EB_HD fe fe_sqr(const fe& a) {
+  u32 t[16];
+  fe_sqr_wide(t, a.v);
+  fe r;
+  fe_reduce512(r.v, t);
+  return r;
+}
+
+EB_HD fe fe_add(const fe& a, const fe& b) {
+  fe r;
+  u32 cy = add_n<8>(r.v, a.v, b.v);
+  cy = fe_addc_k(r.v, cy);
+  // second wrap only when a,b were both >= 2^256 - c - eps: value now < 2^33
+  u64 c = (u64)r.v[0] + (cy ? K256_C0 : 0u);
+  r.v[0] = (u32)c; c >>= 32;
+  r.v[1] += (u32)c + cy;
+  return r;
+}
+
+EB_HD fe fe_sub(const fe& a, const fe& b) {
+  fe r;
+  u32 bw = sub_n<8>(r.v, a.v, b.v);
+  u32 t[8] = {bw ? K256_C0 : 0u, bw, 0, 0, 0, 0, 0, 0};
+  bw = sub_n<8>(r.v, r.v, t);
+  // second borrow: value is now >= 2^256 - c, low 64 bits absorb another -c
+  u64 lo = ((u64)r.v[1] << 32) | r.v[0];
+  lo -= bw ? (((u64)1 << 32) + K256_C0) : 0;
+  r.v[0] = (u32)lo; r.v[1] = (u32)(lo >> 32);
+  return r;
+}
+
+EB_HD fe fe_neg(const fe& a) { return fe_sub(fe_zero(), a); }
+
+// r = a * k for a small constant k (k <= 2^16).
+EB_HD fe fe_mul_small(const fe& a, u32 k) {
+  fe r;
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    c += (u64)a.v[j] * k;
+    r.v[j] = (u32)c; c >>= 32;
+  }
+  // top = c < k : fold top * (2^32 + 977)
+  u32 top = (u32)c;
+  u32 t[8] = {0, top, 0, 0, 0, 0, 0, 0};
+  u64 m = (u64)top * K256_C0;  // < 2^26
+  t[0] = (u32)m;
+  t[1] += (u32)(m >> 32);
+  u32 cy = add_n<8>(r.v, r.v, t);
+  u64 c2 = (u64)r.v[0] + (cy ? K256_C0 : 0u);
+  r.v[0] = (u32)c2; c2 >>= 32;
+  r.v[1] += (u32)c2 + cy;
+  return r;
+}
+
+EB_HD fe fe_dbl(const fe& a) { return fe_add(a, a); }
+
+// p as limbs
+EB_HD void fe_p(u32* p) {
+  p[0] = 0xFFFFFC2Fu; p[1] = 0xFFFFFFFEu;
+  for (int i = 2; i < 8; i++) p[i] = 0xFFFFFFFFu;
+}
+
+// canonical residue in [0,p)  (what bn.js fromRed() exposes)
+EB_HD fe fe_normalize(const fe& a) {
+  u32 p[8]; fe_p(p);
+  fe r;
+  u32 bw = sub_n<8>(r.v, a.v, p);
+  cmov_n<8>(r.v, a.v, bw != 0);
+  return r;
+}
+
+// a == 0 (mod p) for a weakly reduced a
+EB_HD bool fe_is_zero(const fe& a) {
+  u32 o = 0, n = 0xFFFFFFFFu;
+#pragma unroll
+  for (int i = 2; i < 8; i++) { o |= a.v[i]; n &= a.v[i]; }
+  bool z = (o | a.v[0] | a.v[1]) == 0;
+  bool isp = (n == 0xFFFFFFFFu) && a.v[1] == 0xFFFFFFFEu && a.v[0] == 0xFFFFFC2Fu;
+  return z || isp;
+}
+
+EB_HD bool fe_eq(const fe& a, const fe& b) { return fe_is_zero(fe_sub(a, b)); }
+
+EB_HD bool fe_is_odd(const fe& a) { return fe_normalize(a).v[0] & 1; }
+
+EB_HD fe fe_cmov(const fe& a, const fe& b, bool c) {  // c ? b : a
+  fe r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c ? b.v[i] : a.v[i];
+  return r;
+}
+
+// Load a 32-byte big-endian value and reduce mod p (reference: `toRed` ->
+// Red.convertTo, dist:7292-7296; quirk Q2: coordinates >= p are accepted).
+EB_HD fe fe_from_be(const uint8_t* p32) {
+  fe r;
+  load_be<8>(r.v, p32);
+  return r;  // already in [0, 2^256): a valid weak representative
+}
+
+// a^e for the fixed exponents the path needs, by square-and-multiply on the
+// exponent's bits (MSB first).  e is given as 8 limbs.
+EB_HD fe fe_pow(const fe& a, const u32* e) {
+  fe r = fe_one();
+  bool started = false;
+  for (int i = 255; i >= 0; i--) {
+    if (started) r = fe_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      r = started ? fe_mul(r, a) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+
+// a^(p-2)  (0 -> 0, matching bn.js _invmp(0) == 0, dist:6568-6579)
+EB_HD fe fe_inv(const fe& a) {
+  u32 e[8]; fe_p(e);
+  e[0] -= 2;
+  return fe_pow(a, e);
+}
+
+// sqrt candidate a^((p+1)/4)  (Red.sqrt fast path for p = 3 mod 4, dist:7183-7187)
+EB_HD fe fe_sqrt_candidate(const fe& a) {
+  // (p+1)/4 = 2^254 - 2^30 - 244
+  u32 e[8] = {0xBFFFFF0Cu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu,
+              0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x3FFFFFFFu};
+  return fe_pow(a, e);
+}
+
+}  // namespace eb

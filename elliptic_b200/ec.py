@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's ECDSA object for the accelerated path.
+
+`EC(name)` corresponds to `new elliptic.ec(name)` (lib/elliptic/ec/index.js:13-40);
+`verify(msg, sig, key)` keeps the reference's argument forms and error
+behaviour (ec/index.js:188-229) and `verify_batch` is the new batch entry
+point (`EC#verifyBatch(msgs, sigs, pubs) -> Uint8Array`).  Parsing
+(hex / byte arrays / DER / SEC1) is done here exactly as the reference's JS
+does it; all curve arithmetic happens in libelliptic_b200.so on the GPU.
+"""
+import ctypes
+import re
+
+import numpy as np
+
+from . import _native as nat
+
+_CURVES = {
+    "secp256k1": dict(id=nat.CURVE_SECP256K1, len=32,
+                      n=0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141),
+}
+
+
+class EllipticError(Exception):
+    """An `Error` the reference would have thrown (message = the JS message)."""
+
+
+class NeedsReferencePath(EllipticError):
+    """The reference's result for this item is not a group-law function of the
+    inputs (un-validated off-curve public key); the engine does
+    not guess -- run the reference's single-item path for it."""
+
+
+_THROW_MSG = {
+    nat.ST_THROW_INVALID_POINT: "invalid point",
+    nat.ST_THROW_NOT_VALIDATED: "public point not validated",
+    nat.ST_THROW_ASSERT: "Assertion failed",
+    nat.ST_THROW_POINT_FORMAT: "Unknown point format",
+}
+
+
+def _to_array(msg, enc=None):
+    """minimalistic-crypto-utils.toArray (reference dist/elliptic.js:8847-8876)."""
+    if isinstance(msg, (bytes, bytearray)):
+        return bytes(msg)
+    if isinstance(msg, (list, tuple, np.ndarray)):
+        return bytes(int(b) & 0xFF for b in msg)
+    if not msg:
+        return b""
+    if isinstance(msg, str):
+        if enc == "hex":
+            msg = re.sub(r"[^a-zA-Z0-9]+", "", msg)
+            if len(msg) % 2:
+                msg = "0" + msg
+            out = bytearray()
+            for i in range(0, len(msg), 2):
+                try:
+                    out.append(int(msg[i:i + 2], 16))
+                except ValueError:
+                    out.append(0)
+            return bytes(out)
+        out = bytearray()
+        for ch in msg:
+            c = ord(ch)
+            if c >> 8:
+                out.append(c >> 8)
+            out.append(c & 0xFF)
+        return bytes(out)
+    raise TypeError("unsupported input form")
+
+
+def _bn(v):
+    """`new BN(v, 16)` for int / hex string / byte array."""
+    if isinstance(v, int):
+        return v
+    if isinstance(v, str):
+        return int(v, 16) if v else 0
+    return int.from_bytes(bytes(v), "big")
+
+
+def parse_der(data):
+    """Signature._importDER (ec/signature.js:73-134).  Returns (r, s) or None."""
+    n = len(data)
+    pos = 0
+
+    def byte(i):
+        return data[i] if 0 <= i < n else None
+
+    def get_length():
+        nonlocal pos
+        initial = byte(pos)
+        pos += 1
+        if initial is None:
+            return 0
+        if not (initial & 0x80):
+            return initial
+        octets = initial & 0xF
+        if octets == 0 or octets > 4:
+            return None
+        if byte(pos) == 0:
+            return None
+        val = 0
+        off = pos
+        for _ in range(octets):
+            val = ((val << 8) | (byte(off) or 0)) & 0xFFFFFFFF
+            off += 1
+        if val <= 0x7F:
+            return None
+        pos = off
+        return val
+
+    if byte(pos) != 0x30:
+        return None
+    pos += 1
+    ln = get_length()
+    if ln is None or ln + pos != n:
+        return None
+    if byte(pos) != 0x02:
+        return None
+    pos += 1
+    rlen = get_length()
+    if rlen is None or ((byte(pos) or 0) & 0x80):
+        return None
+    r = data[pos:pos + rlen]
+    pos += rlen
+    if byte(pos) != 0x02:
+        return None
+    pos += 1
+    slen = get_length()
+    if slen is None or n != slen + pos or ((byte(pos) or 0) & 0x80):
+        return None
+    s = data[pos:pos + slen]
+    for v in (r, s):
+        if len(v) and v[0] == 0 and not (len(v) > 1 and v[1] & 0x80):
+            return None
+    return int.from_bytes(r, "big"), int.from_bytes(s, "big")
+
+
+class EC:
+    def __init__(self, curve="secp256k1", device=0):
+        if curve not in _CURVES:
+            raise EllipticError("Unknown curve " + str(curve))   # ec/index.js:19-20
+        self.name = curve
+        self._c = _CURVES[curve]
+        self.n = self._c["n"]
+        self._len = self._c["len"]
+        self._device = device
+
+    # ---- reference-compatible scalar preparation (host side, cheap) -------------
+    def _truncate_to_n(self, msg, msg_bit_length=None):
+        """EC._truncateToN (ec/index.js:81-108) up to, but not including, the
+        conditional `- n` (the engine reduces mod n itself)."""
+        if isinstance(msg, int):
+            v = msg
+            byte_length = (v.bit_length() + 7) // 8
+        elif isinstance(msg, str):
+            byte_length = (len(msg) + 1) >> 1
+            v = int(msg, 16) if msg else 0
+        else:
+            b = _to_array(msg)
+            byte_length = len(b)
+            v = int.from_bytes(b, "big")
+        bit_length = byte_length * 8 if msg_bit_length is None else msg_bit_length
+        delta = bit_length - self.n.bit_length()
+        if delta > 0:
+            v >>= delta
+        if v >= self.n:
+            v -= self.n
+        return v
+
+    def _signature(self, sig):
+        """new Signature(sig, 'hex') (ec/signature.js:8-22)."""
+        if isinstance(sig, dict):
+            if not (sig.get("r") and sig.get("s")):
+                raise EllipticError("Signature without r or s")
+            return _bn(sig["r"]), _bn(sig["s"])
+        if hasattr(sig, "r") and hasattr(sig, "s"):
+            return int(sig.r), int(sig.s)
+        rs = parse_der(_to_array(sig, "hex"))
+        if rs is None:
+            raise EllipticError("Signature without r or s")
+        return rs
+
+    def _public(self, key, enc=None):
+        """KeyPair._importPublic (ec/key.js:84-99) -> (fmt, bytes)."""
+        ln = self._len
+        if isinstance(key, dict) and (key.get("x") or key.get("y")):
+            if not (key.get("x") and key.get("y")):
+                raise EllipticError("Need both x and y coordinate")
+            x, y = _bn(key["x"]), _bn(key["y"])
+            if x < 0 or y < 0:
+                raise EllipticError("red works only with positives")
+            # toRed reduces oversize coordinates mod p (short.js:258-268); the engine
+            # does that for anything that fits the wire width, wider values here.
+            if x >> (8 * ln) or y >> (8 * ln):
+                p = 2**256 - 2**32 - 977
+                x %= p
+                y %= p
+            return nat.PUB_XY, x.to_bytes(ln, "big") + y.to_bytes(ln, "big")
+        b = _to_array(key, enc)
+        if len(b) and b[0] in (4, 6, 7) and len(b) - 1 == 2 * ln:
+            if (b[0] == 6 and b[-1] % 2 != 0) or (b[0] == 7 and b[-1] % 2 != 1):
+                raise EllipticError("Assertion failed")            # base.js:278-281
+            return nat.PUB_XY, b[1:]
+        if len(b) and b[0] in (2, 3) and len(b) - 1 == ln:
+            return nat.PUB_SEC1_33, b
+        raise EllipticError("Unknown point format")                # base.js:291
+
+    # ---- batch entry points ---------------------------------------------------
+    def verify_batch_packed(self, e, r, s, pub, pub_fmt=nat.PUB_XY):
+        """Packed form: e, r, s are (n, len) uint8 arrays (big-endian), pub is
+        (n, 2*len).  Returns the per-item status bytes (see _native.ST_*)."""
+        lib = nat.init(self._device)
+        e = np.ascontiguousarray(e, dtype=np.uint8)
+        r = np.ascontiguousarray(r, dtype=np.uint8)
+        s = np.ascontiguousarray(s, dtype=np.uint8)
+        pub = np.ascontiguousarray(pub, dtype=np.uint8)
+        n = e.shape[0]
+        assert e.shape == (n, self._len) and r.shape == e.shape and s.shape == e.shape
+        status = np.empty(n, dtype=np.uint8)
+        nat.check(lib.eb200_ecdsa_verify_batch(
+            self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data, pub.ctypes.data,
+            pub_fmt, status.ctypes.data))
+        return status
+
+    def verify_batch(self, msgs, sigs, keys, enc=None, msg_bit_length=None):
+        """EC#verifyBatch: lists of the reference's own argument forms.
+        Returns a uint8 array of statuses; items whose *parsing* throws in the
+        reference raise here, like a loop over `verify` would at that item."""
+        n = len(msgs)
+        ln = self._len
+        e = np.zeros((n, ln), np.uint8)
+        r = np.zeros((n, ln), np.uint8)
+        s = np.zeros((n, ln), np.uint8)
+        pub = np.zeros((n, 2 * ln), np.uint8)
+        early = {}
+        for i in range(n):
+            ev = self._truncate_to_n(msgs[i], msg_bit_length)
+            fmt, pb = self._public(keys[i], enc)
+            if fmt != nat.PUB_XY:
+                raise EllipticError("compressed keys: use verify_batch_packed with PUB_SEC1_33")
+            rv, sv = self._signature(sigs[i])
+            if rv < 1 or rv >= self.n or sv < 1 or sv >= self.n:
+                early[i] = nat.ST_FALSE       # ec/index.js:199-202
+                rv = sv = 0
+            e[i] = np.frombuffer(ev.to_bytes(ln, "big"), np.uint8)
+            r[i] = np.frombuffer(rv.to_bytes(ln, "big"), np.uint8)
+            s[i] = np.frombuffer(sv.to_bytes(ln, "big"), np.uint8)
+            pub[i] = np.frombuffer(pb, np.uint8)
+        st = self.verify_batch_packed(e, r, s, pub)
+        for i, v in early.items():
+            st[i] = v
+        return st
+
+    def verify(self, msg, signature, key, enc=None, options=None):
+        """EC.prototype.verify (ec/index.js:188-229): bool, or raises."""
+        mbl = (options or {}).get("msgBitLength")
+        st = int(self.verify_batch([msg], [signature], [key], enc, mbl)[0])
+        if st == nat.ST_TRUE:
+            return True
+        if st == nat.ST_FALSE:
+            return False
+        if st == nat.ST_NEEDS_HOST:
+            raise NeedsReferencePath("public key is not on the curve; the reference does not validate it")
+        raise EllipticError(_THROW_MSG.get(st, "status %d" % st))

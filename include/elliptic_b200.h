@@ -1,0 +1,101 @@
+/* elliptic_b200.h -- C ABI of libelliptic_b200.so, the drop-in boundary.
+ *
+ * The reference (indutny/elliptic, pure JavaScript) has no FFI of its own
+ * (SURVEY.md 8b); these are the entry points an N-API addon for
+ * `require('elliptic')` binds so that whole batches of the reference's
+ * single-item calls run on B200 GPUs.  Each function names the reference
+ * method whose per-item semantics it reproduces bit-exactly.
+ *
+ * Conventions: field elements / scalars are fixed-width big-endian byte
+ * strings (32 bytes for secp256k1, the reference's toArray('be', len),
+ * lib/elliptic/curve/base.js:298-306); arrays are item-major and contiguous
+ * (item i of `r` is r[32*i .. 32*i+31]).  The caller owns every buffer.
+ * Every function returns EB200_OK (0) or a negative error code; nothing
+ * throws or aborts.  Per-item outcomes are written to `status`.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry
+ * point returns EB200_ERR_NO_DEVICE.
+ */
+#ifndef ELLIPTIC_B200_H
+#define ELLIPTIC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EB200_OK 0
+#define EB200_ERR_NO_DEVICE (-1)   /* no CUDA device / driver */
+#define EB200_ERR_CUDA (-2)        /* a CUDA call failed: eb200_last_error() */
+#define EB200_ERR_ARG (-3)         /* bad argument (NULL buffer, unknown curve/format) */
+#define EB200_ERR_NOT_INIT (-4)    /* eb200_init() has not succeeded */
+#define EB200_ERR_UNSUPPORTED (-5) /* curve / format not built yet */
+
+/* per-item status byte: what the reference's call would have done */
+#define EB200_ST_FALSE 0                /* returned false */
+#define EB200_ST_TRUE 1                 /* returned true */
+#define EB200_ST_THROW_INVALID_POINT 2  /* threw Error('invalid point')  short.js:195, edwards.js:84 */
+#define EB200_ST_THROW_NOT_VALIDATED 3  /* threw Error('public point not validated')  ec/key.js:104 */
+#define EB200_ST_NEEDS_HOST 4           /* result is not a group-law function of the inputs (off-curve
+                                           un-validated key): caller must run the reference's
+                                           own single-item path for this item */
+#define EB200_ST_THROW_ASSERT 5         /* threw Error('Assertion failed') (bn.js sqrt / hybrid parity) */
+#define EB200_ST_THROW_POINT_FORMAT 6   /* threw Error('Unknown point format')  base.js:291 */
+
+/* curve ids (names of lib/elliptic/curves.js presets) */
+#define EB200_CURVE_SECP256K1 1
+#define EB200_CURVE_P256 2
+#define EB200_CURVE_P384 3
+#define EB200_CURVE_ED25519 4
+#define EB200_CURVE_CURVE25519 5
+
+/* public-key encodings accepted by eb200_ecdsa_verify_batch (KeyPair._importPublic,
+ * lib/elliptic/ec/key.js:84-99 -> BaseCurve.decodePoint, curve/base.js:270-292) */
+#define EB200_PUB_XY 0          /* {x, y}: 2*len bytes per item, NOT validated (as the reference) */
+#define EB200_PUB_SEC1_65 1     /* 04|06|07 || x || y : 1+2*len bytes per item */
+#define EB200_PUB_SEC1_33 2     /* 02|03 || x : 1+len bytes per item (pointFromX, short.js:187-204) */
+
+typedef struct eb200_timing {
+  float h2d_ms;     /* host->device copies of the last host-buffer call */
+  float kernel_ms;  /* all kernels of the last call (CUDA events on the launch stream) */
+  float d2h_ms;     /* device->host copy of the results */
+  float main_kernel_ms; /* the dominant kernel only */
+  uint32_t launches; /* kernels launched by the last call */
+} eb200_timing;
+
+/* Select device `device` (CUDA ordinal), build the fixed-base tables.  Idempotent per device. */
+int eb200_init(int device);
+int eb200_shutdown(void);
+const char* eb200_strerror(int code);
+const char* eb200_last_error(void);   /* text of the last CUDA error on this thread's context */
+int eb200_last_timing(eb200_timing* out);
+
+/* Batch of EC.prototype.verify (lib/elliptic/ec/index.js:188-229) for `curve`.
+ *   e   : n x len  message hashes already truncated as _truncateToN does for a len-byte
+ *                  input (ec/index.js:81-108); values >= n are accepted like the reference
+ *   r,s : n x len  signature halves (Signature{r,s}, ec/signature.js:8-22)
+ *   pub : n x (pub_fmt-dependent) public keys
+ *   status : n bytes out
+ * Host pointers; copies are done internally on the library's stream. */
+int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r,
+                             const uint8_t* s, const uint8_t* pub, uint32_t pub_fmt,
+                             uint8_t* status);
+
+/* Same, with DEVICE pointers and a caller-supplied CUDA stream (cudaStream_t cast to void*;
+ * NULL = the library's stream).  Asynchronous: the caller synchronises the stream.
+ * `workspace` must hold eb200_ecdsa_verify_workspace_bytes(curve, n) bytes of device memory. */
+size_t eb200_ecdsa_verify_workspace_bytes(int curve, size_t n);
+int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r,
+                                 const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
+                                 uint8_t* d_status, void* d_workspace, void* stream);
+
+/* Self-test hooks used by the parity tests (device arithmetic vs the oracle).
+ * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_small(b[0]), 6 normalize, 7 inv, 8 sqrt candidate.
+ * a, b, out: n x 8 little-endian 32-bit limbs (host pointers). */
+int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* Copy the fixed-base table of `curve` to the host (n_words 32-bit words available). */
+int eb200_selftest_gtab(int curve, uint32_t* out, size_t n_words);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

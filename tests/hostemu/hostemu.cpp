@@ -1,0 +1,69 @@
+// Host emulation of the kernel bodies -- TEST INFRASTRUCTURE ONLY.
+// Compiles the same .cuh bodies the CUDA kernels use with their portable C++
+// fallbacks so the kernel *logic* (recoding, tables, exceptional cases, status
+// codes) can be checked against the oracle on a CPU-only box.  The product
+// library (libelliptic_b200.so) never contains or calls this code.
+#include <vector>
+#include <cstring>
+#include "../../elliptic_b200/csrc/ecdsa_k256_body.cuh"
+using namespace eb;
+
+extern "C" {
+
+// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_small(k=b[0]), 6 normalize, 7 inv, 8 sqrt_candidate
+void he_fe_op(int op, const u32* a, const u32* b, u32* out) {
+  fe A = load_fe(a), B = load_fe(b), R;
+  switch (op) {
+    case 0: R = fe_mul(A, B); break;
+    case 1: R = fe_sqr(A); break;
+    case 2: R = fe_add(A, B); break;
+    case 3: R = fe_sub(A, B); break;
+    case 4: R = fe_neg(A); break;
+    case 5: R = fe_mul_small(A, b[0]); break;
+    case 6: R = fe_normalize(A); break;
+    case 7: R = fe_inv(A); break;
+    case 8: R = fe_sqrt_candidate(A); break;
+    default: R = fe_zero();
+  }
+  store_fe(out, R);
+}
+
+void he_sc_mont_mul(const u32* a, const u32* b, u32* out) { sc_mont_mul(out, a, b); }
+
+void he_glv(const u32* k, u32* m1, int* n1, u32* m2, int* n2) {
+  bool a, b;
+  glv_split_odd(k, m1, &a, m2, &b);
+  *n1 = a; *n2 = b;
+}
+
+void he_gtab(u32* out /* 32*128*16 */, int jlo, int jhi) {
+  for (int j = jlo; j < jhi; j++)
+    for (int i = 0; i < GTAB_ENTRIES; i++) gtab_entry(j, i, out + ((size_t)j * GTAB_ENTRIES + i) * 16);
+}
+
+// Fast gtab build for tests: incremental instead of per-entry scalar mults.
+void he_gtab_fast(u32* out) {
+  ge_jac base = jac_from_aff(k256_G());
+  for (int j = 0; j < GTAB_WINDOWS; j++) {
+    ge_aff b = jac_to_aff(base);
+    ge_jac d = jac_dbl(jac_from_aff(b));
+    ge_jac acc = jac_from_aff(b);
+    for (int i = 0; i < GTAB_ENTRIES; i++) {
+      ge_aff r = jac_to_aff(acc);
+      r.x = fe_normalize(r.x); r.y = fe_normalize(r.y);
+      store_fe(out + ((size_t)j * GTAB_ENTRIES + i) * 16, r.x);
+      store_fe(out + ((size_t)j * GTAB_ENTRIES + i) * 16 + 8, r.y);
+      acc = jac_add_inl(acc, d);
+    }
+    for (int k = 0; k < 8; k++) base = jac_dbl(base);
+  }
+}
+
+void he_verify(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
+               const u32* gtab, uint8_t* status) {
+  std::vector<u32> ws((size_t)PREP_WORDS * N), scratch((size_t)8 * N), qtab((size_t)QTAB_WORDS * N);
+  size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
+  for (size_t t = 0; t < T; t++) prep_thread(t, T, N, e, r, s, ws.data(), scratch.data());
+  for (size_t i = 0; i < N; i++) status[i] = verify_item(i, N, pub, r, ws.data(), gtab, qtab.data());
+}
+}
