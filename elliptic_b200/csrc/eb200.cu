@@ -74,6 +74,7 @@ struct Ctx {
   uint8_t* d_status = nullptr; size_t d_status_cap = 0;
   cudaEvent_t ev[6] = {};
   eb200_timing timing = {};
+  bool dev_timing_pending = false;
 };
 Ctx g;
 std::mutex g_mu;
@@ -179,6 +180,14 @@ int eb200_shutdown(void) {
 
 int eb200_last_timing(eb200_timing* out) {
   if (!out) return EB200_ERR_ARG;
+  if (g.dev_timing_pending) {
+    // device-pointer call: the caller has synchronised its stream by now
+    g.timing = eb200_timing{};
+    if (cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]) != cudaSuccess) return EB200_ERR_CUDA;
+    if (cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]) != cudaSuccess) return EB200_ERR_CUDA;
+    g.timing.launches = 2;
+    g.dev_timing_pending = false;
+  }
   *out = g.timing;
   return EB200_OK;
 }
@@ -196,7 +205,13 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
   if (pub_fmt != EB200_PUB_XY) return EB200_ERR_UNSUPPORTED;
   if (n && (!d_e || !d_r || !d_s || !d_pub || !d_status || !d_workspace)) return EB200_ERR_ARG;
   cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
-  return launch_k256_verify(n, d_e, d_r, d_s, d_pub, d_status, (uint8_t*)d_workspace, st, nullptr, nullptr);
+  // events on the caller's stream: eb200_last_timing() reports them once the stream has been synchronised
+  CK(cudaEventRecord(g.ev[1], st));
+  int rc = launch_k256_verify(n, d_e, d_r, d_s, d_pub, d_status, (uint8_t*)d_workspace, st, g.ev[4], g.ev[5]);
+  if (rc) return rc;
+  CK(cudaEventRecord(g.ev[2], st));
+  g.dev_timing_pending = true;
+  return EB200_OK;
 }
 
 int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r,
@@ -231,6 +246,7 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(g.ev[3], st));
   CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
   cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
   cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
   cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);

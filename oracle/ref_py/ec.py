@@ -59,12 +59,14 @@ class KeyPair:
         """ec/key.js:84-99.  NB: {x,y} and uncompressed keys are NOT checked
         to be on the curve (quirk Q1)."""
         c = self.ec.curve
-        if isinstance(key, dict) and (key.get("x") or key.get("y")):
+        # JS truthiness: a BN object (even 0) and a non-empty string are truthy
+        tr = lambda v: v is not None and v != "" and not (isinstance(v, (bytes, list)) and len(v) == 0)
+        if isinstance(key, dict) and (tr(key.get("x")) or tr(key.get("y"))):
             if c.type == "mont":
-                ref_assert(key.get("x"), "Need x coordinate")
+                ref_assert(tr(key.get("x")), "Need x coordinate")
                 self.pub = c.point(_bn(key["x"]), 1)
                 return
-            ref_assert(key.get("x") and key.get("y"), "Need both x and y coordinate")
+            ref_assert(tr(key.get("x")) and tr(key.get("y")), "Need both x and y coordinate")
             self.pub = c.point(_bn(key["x"]), _bn(key["y"]))
             return
         if hasattr(key, "curve") and hasattr(key, "is_infinity"):
