@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libelliptic_b200.so")
+# EB200_LIB lets the tuning scripts load an alternative build of the same library
+LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(_HERE, "libelliptic_b200.so")
 
 OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_NOT_INIT, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ST_FALSE, ST_TRUE, ST_THROW_INVALID_POINT, ST_THROW_NOT_VALIDATED, ST_NEEDS_HOST, ST_THROW_ASSERT, \
@@ -18,7 +19,7 @@ PUB_XY, PUB_SEC1_65, PUB_SEC1_33 = 0, 1, 2
 EXPORTS = [
     "eb200_init", "eb200_shutdown", "eb200_strerror", "eb200_last_error", "eb200_last_timing",
     "eb200_ecdsa_verify_batch", "eb200_ecdsa_verify_workspace_bytes", "eb200_ecdsa_verify_batch_dev",
-    "eb200_selftest_fe", "eb200_selftest_gtab",
+    "eb200_selftest_fe", "eb200_selftest_gtab", "eb200_selftest_gtab_dims",
 ]
 
 

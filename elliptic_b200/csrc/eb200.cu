@@ -12,9 +12,11 @@ using namespace eb;
 
 // ---------------------------------------------------------------------------
 // kernels
-__global__ void __launch_bounds__(GTAB_ENTRIES) k256_gtab_kernel(u32* gtab) {
-  int j = blockIdx.x, idx = threadIdx.x;
-  gtab_entry(j, idx, gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16);
+__global__ void __launch_bounds__(128) k256_gtab_kernel(u32* gtab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)GTAB_WINDOWS * GTAB_ENTRIES) return;
+  int j = (int)(t / GTAB_ENTRIES), idx = (int)(t % GTAB_ENTRIES);
+  gtab_entry(j, idx, gtab + t * 16);
 }
 
 __global__ void __launch_bounds__(128) k256_prep_kernel(size_t N, const uint8_t* __restrict__ e,
@@ -30,7 +32,7 @@ __global__ void __launch_bounds__(128) k256_prep_kernel(size_t N, const uint8_t*
 #define EB_VERIFY_BLOCK 128
 #endif
 #ifndef EB_VERIFY_MINBLOCKS
-#define EB_VERIFY_MINBLOCKS 4
+#define EB_VERIFY_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(EB_VERIFY_BLOCK, EB_VERIFY_MINBLOCKS)
 k256_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __restrict__ r,
@@ -156,7 +158,7 @@ int eb200_init(int device) {
   for (int i = 0; i < 6; i++) if (!g.ev[i]) CK(cudaEventCreate(&g.ev[i]));
   if (g.gtab_k256) { cudaFree(g.gtab_k256); g.gtab_k256 = nullptr; }
   CK(cudaMalloc(&g.gtab_k256, (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 16 * 4));
-  k256_gtab_kernel<<<GTAB_WINDOWS, GTAB_ENTRIES, 0, g.stream>>>(g.gtab_k256);
+  k256_gtab_kernel<<<(unsigned)(((size_t)GTAB_WINDOWS * GTAB_ENTRIES + 127) / 128), 128, 0, g.stream>>>(g.gtab_k256);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   g.device = device;
@@ -204,7 +206,7 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
   if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
   if (pub_fmt != EB200_PUB_XY) return EB200_ERR_UNSUPPORTED;
   if (n && (!d_e || !d_r || !d_s || !d_pub || !d_status || !d_workspace)) return EB200_ERR_ARG;
-  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  cudaStream_t st = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere in CUDA
   // events on the caller's stream: eb200_last_timing() reports them once the stream has been synchronised
   CK(cudaEventRecord(g.ev[1], st));
   int rc = launch_k256_verify(n, d_e, d_r, d_s, d_pub, d_status, (uint8_t*)d_workspace, st, g.ev[4], g.ev[5]);
@@ -270,6 +272,13 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
   CK(cudaStreamSynchronize(g.stream));
   CK(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
+  return EB200_OK;
+}
+
+int eb200_selftest_gtab_dims(int curve, int* windows, int* entries, int* wbits) {
+  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (!windows || !entries || !wbits) return EB200_ERR_ARG;
+  *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W;
   return EB200_OK;
 }
 

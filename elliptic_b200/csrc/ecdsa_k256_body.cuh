@@ -42,7 +42,13 @@ constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG1 = 4, FL_NEG2 = 8;
 constexpr int PREP_BATCH = 16;          // items per thread in the batched inversion
 constexpr int QTAB_ENTRIES = 8;         // odd multiples 1,3,..,15
 constexpr int QTAB_WORDS = QTAB_ENTRIES * 24;  // per item: (x, y, beta*x) x 8
-constexpr int GTAB_WINDOWS = 32, GTAB_ENTRIES = 128;  // (2i+1) * 2^(8j) * G
+#ifndef EB_GW
+#define EB_GW 16                         // fixed-base window width in bits (r01 sweep: 8/11/13/16 -> 25.7/24.6/24.1/23.7 ms)
+#endif
+constexpr int GTAB_W = EB_GW;
+constexpr int GTAB_WINDOWS = (255 + GTAB_W - 1) / GTAB_W;     // digits of m = (u1'-1)/2 (255 bits)
+constexpr int GTAB_ENTRIES = 1 << (GTAB_W - 1);               // (2i+1) * 2^(W*j) * G, i < 2^(W-1)
+static_assert(255 - GTAB_W * (GTAB_WINDOWS - 1) <= GTAB_W - 1, "top digit 2m+1 must stay below 2^W");
 
 struct madd_out { ge_jac r; fe h; };
 
@@ -89,14 +95,14 @@ EB_HD ge_aff k256_G() {
 }
 
 // ---------------------------------------------------------------------------
-// G table entry (j, idx) = (2*idx+1) * 2^(8j) * G, affine, normalized.
+// G table entry (j, idx) = (2*idx+1) * 2^(W*j) * G, affine, normalized.
 EB_HD void gtab_entry(int j, int idx, u32* out16) {
   ge_jac b = jac_from_aff(k256_G());
-  for (int k = 0; k < 8 * j; k++) b = jac_dbl(b);
+  for (int k = 0; k < GTAB_W * j; k++) b = jac_dbl(b);
   ge_aff base = jac_to_aff(b);
-  u32 s = 2 * idx + 1;  // 8-bit odd scalar
+  u32 s = 2 * idx + 1;  // W-bit odd scalar
   ge_jac acc = jac_infinity();
-  for (int k = 7; k >= 0; k--) {
+  for (int k = GTAB_W - 1; k >= 0; k--) {
     acc = jac_dbl(acc);
     if ((s >> k) & 1) acc = jac_madd(acc, base);
   }
@@ -237,7 +243,7 @@ EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t*
   ge_jac acc = jac_infinity();
   for (int w = 32; w >= 0; w--) {
     if (w != 32)
-      for (int d = 0; d < 4; d++) acc = jac_dbl(acc);
+      for (int d = 0; d < 4; d++) acc = jac_dbl(acc);   // (the top window starts from its first table entry)
     for (int h = 0; h < 2; h++) {
       u32 word = ws[(size_t)((h ? 13 : 8) + (w >> 3)) * N + i];
       u32 nib = (word >> (4 * (w & 7))) & 15;
@@ -247,18 +253,24 @@ EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t*
       ge_aff P;
       P.x = load_fe(tab + 24 * idx + (h ? 16 : 0));
       P.y = load_fe(tab + 24 * idx + 8);
-      acc = jac_madd(acc, aff_neg_if(P, neg));
+      P = aff_neg_if(P, neg);
+      if (w == 32 && h == 0) acc = jac_from_aff(P);
+      else acc = jac_madd(acc, P);
     }
   }
   // back to the real curve: Z *= Zg
   acc.z = fe_mul(acc.z, zglobal);
 
-  // ---- u1*G from the fixed table: 32 windows of 8 bits, regular signed-odd digits
+  // ---- u1*G from the fixed table: GTAB_WINDOWS windows of GTAB_W bits, regular signed-odd digits
   for (int j = 0; j < GTAB_WINDOWS; j++) {
-    u32 word = ws[(size_t)(j >> 2) * N + i];
-    u32 byte = (word >> (8 * (j & 3))) & 255;
-    bool dneg = (j != 31) && (byte < 128);
-    u32 idx = (j == 31) ? (byte & 127) : (dneg ? 127 - byte : byte - 128);
+    const int pos = GTAB_W * j;
+    u32 lo = ws[(size_t)(pos >> 5) * N + i];
+    u32 hi = ((pos >> 5) < 7) ? ws[(size_t)((pos >> 5) + 1) * N + i] : 0u;
+    u64 both = ((u64)hi << 32) | lo;
+    u32 chunk = (u32)(both >> (pos & 31)) & ((1u << GTAB_W) - 1);
+    const u32 half = 1u << (GTAB_W - 1);
+    bool dneg = (j != GTAB_WINDOWS - 1) && (chunk < half);
+    u32 idx = (j == GTAB_WINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
     bool neg = dneg != ((flags & FL_NEGG) != 0);
     const u32* ent = gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16;
     ge_aff P;

@@ -81,7 +81,7 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
                              uint8_t* status);
 
 /* Same, with DEVICE pointers and a caller-supplied CUDA stream (cudaStream_t cast to void*;
- * NULL = the library's stream).  Asynchronous: the caller synchronises the stream.
+ * NULL = the CUDA default stream).  Asynchronous: the caller synchronises the stream.
  * `workspace` must hold eb200_ecdsa_verify_workspace_bytes(curve, n) bytes of device memory. */
 size_t eb200_ecdsa_verify_workspace_bytes(int curve, size_t n);
 int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r,
@@ -92,6 +92,8 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
  * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_small(b[0]), 6 normalize, 7 inv, 8 sqrt candidate.
  * a, b, out: n x 8 little-endian 32-bit limbs (host pointers). */
 int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
+/* Geometry of the fixed-base table: entry (j, i) = (2i+1) * 2^(wbits*j) * G, 16 words (x||y limbs). */
+int eb200_selftest_gtab_dims(int curve, int* windows, int* entries, int* wbits);
 /* Copy the fixed-base table of `curve` to the host (n_words 32-bit words available). */
 int eb200_selftest_gtab(int curve, uint32_t* out, size_t n_words);
 

@@ -41,6 +41,8 @@ void he_gtab(u32* out /* 32*128*16 */, int jlo, int jhi) {
     for (int i = 0; i < GTAB_ENTRIES; i++) gtab_entry(j, i, out + ((size_t)j * GTAB_ENTRIES + i) * 16);
 }
 
+void he_gtab_dims(int* windows, int* entries, int* wbits) { *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W; }
+
 // Fast gtab build for tests: incremental instead of per-entry scalar mults.
 void he_gtab_fast(u32* out) {
   ge_jac base = jac_from_aff(k256_G());
@@ -55,7 +57,7 @@ void he_gtab_fast(u32* out) {
       store_fe(out + ((size_t)j * GTAB_ENTRIES + i) * 16 + 8, r.y);
       acc = jac_add_inl(acc, d);
     }
-    for (int k = 0; k < 8; k++) base = jac_dbl(base);
+    for (int k = 0; k < GTAB_W; k++) base = jac_dbl(base);
   }
 }
 

@@ -71,13 +71,16 @@ def test_fixed_base_table_matches_oracle(native):
     from elliptic_b200 import _native as nat
     from oracle.ref_py.ec import EC
     g = EC("secp256k1").g
-    tab = np.zeros(32 * 128 * 16, np.uint32)
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    nat.check(native.eb200_selftest_gtab_dims(nat.CURVE_SECP256K1, ctypes.byref(W), ctypes.byref(E), ctypes.byref(B)))
+    W, E, B = W.value, E.value, B.value
+    tab = np.zeros(W * E * 16, np.uint32)
     nat.check(native.eb200_selftest_gtab(nat.CURVE_SECP256K1, tab.ctypes.data, tab.size))
-    tab = tab.reshape(32, 128, 2, 8)
+    tab = tab.reshape(W, E, 2, 8)
     rnd = random.Random(5)
-    samples = [(0, 0), (0, 1), (0, 127), (31, 0), (31, 127)] + [(rnd.randrange(32), rnd.randrange(128)) for _ in range(60)]
+    samples = [(0, 0), (0, 1), (0, E - 1), (W - 1, 0), (W - 1, E - 1)] + [(rnd.randrange(W), rnd.randrange(E)) for _ in range(60)]
     for j, i in samples:
-        pt = g.mul(((2 * i + 1) << (8 * j)) % N)
+        pt = g.mul(((2 * i + 1) << (B * j)) % N)
         x, y = ints(tab[j, i])
         assert (x, y) == (pt.x, pt.y), (j, i)
 

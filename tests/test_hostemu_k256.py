@@ -67,7 +67,9 @@ def test_verify_pipeline_against_oracle(he):
     from oracle.ref_py.ec import EC
     from test_gpu_k256 import _edge_items, _expected
     ec = EC("secp256k1")
-    gtab = np.zeros(32 * 128 * 16, np.uint32)
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    he.he_gtab_dims(ctypes.byref(W), ctypes.byref(E), ctypes.byref(B))
+    gtab = np.zeros(W.value * E.value * 16, np.uint32)
     he.he_gtab_fast(gtab.ctypes.data_as(ctypes.c_void_p))
     items = _edge_items(ec, random.Random(77))[::3] + _edge_items(ec, random.Random(78))[-9:]
     n = len(items)
