@@ -1,17 +1,26 @@
 // eb200.cu -- CUDA kernels (sm_100a) and the C ABI of libelliptic_b200.so.
-// See include/elliptic_b200.h for the boundary and ecdsa_k256_body.cuh for the
-// algorithm.  No CPU fallback exists in this library by design.
+// See include/elliptic_b200.h for the boundary, ecdsa_k256_body.cuh (secp256k1) and
+// ecdsa_sw_body.cuh (p256 / p384) for the algorithms.  No CPU fallback exists in this
+// library by design: without a CUDA device every compute entry point fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
+#include "ecdsa_sw_body.cuh"
 
 using namespace eb;
 
+#ifndef EB_VERIFY_BLOCK
+#define EB_VERIFY_BLOCK 128
+#endif
+#ifndef EB_VERIFY_MINBLOCKS
+#define EB_VERIFY_MINBLOCKS 3
+#endif
+
 // ---------------------------------------------------------------------------
-// kernels
+// secp256k1 kernels
 __global__ void __launch_bounds__(128) k256_gtab_kernel(u32* gtab) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (size_t)GTAB_WINDOWS * GTAB_ENTRIES) return;
@@ -28,19 +37,46 @@ __global__ void __launch_bounds__(128) k256_prep_kernel(size_t N, const uint8_t*
   prep_thread(tid, T, N, e, r, s, ws, scratch);
 }
 
-#ifndef EB_VERIFY_BLOCK
-#define EB_VERIFY_BLOCK 128
-#endif
-#ifndef EB_VERIFY_MINBLOCKS
-#define EB_VERIFY_MINBLOCKS 3
-#endif
 __global__ void __launch_bounds__(EB_VERIFY_BLOCK, EB_VERIFY_MINBLOCKS)
 k256_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __restrict__ r,
                    const u32* __restrict__ ws, const u32* __restrict__ gtab,
-                   u32* __restrict__ qtab, uint8_t* __restrict__ status) {
+                   u32* __restrict__ qtab, const uint8_t* __restrict__ pre, uint8_t* __restrict__ status) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (pre && pre[i]) { status[i] = pre[i]; return; }   // the reference throws while importing the key
   status[i] = verify_item(i, N, pub, r, ws, gtab, qtab);
+}
+
+// SEC1 decode (BaseCurve.decodePoint, lib/elliptic/curve/base.js:270-292; pointFromX short.js:187-204)
+// fmt 1: 65-byte 04|06|07 || x || y ; fmt 2: 33-byte 02|03 || x.  Writes x||y (64 B) + a pre-status.
+__global__ void __launch_bounds__(128) k256_decode_pub_kernel(size_t N, const uint8_t* __restrict__ in, u32 fmt,
+                                                              uint8_t* __restrict__ xy, uint8_t* __restrict__ pre) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  uint8_t st = 0;
+  if (fmt == EB200_PUB_SEC1_65) {
+    const uint8_t* p = in + 65 * i;
+    uint8_t tag = p[0];
+    if (tag != 4 && tag != 6 && tag != 7) st = ST_THROW_POINT_FORMAT;
+    else if ((tag == 6 && (p[64] & 1)) || (tag == 7 && !(p[64] & 1))) st = ST_THROW_ASSERT;   // base.js:278-281
+    for (int k = 0; k < 64; k++) xy[64 * i + k] = p[1 + k];
+  } else {
+    const uint8_t* p = in + 33 * i;
+    uint8_t tag = p[0];
+    if (tag != 2 && tag != 3) st = ST_THROW_POINT_FORMAT;
+    fe x = fe_from_be(p + 1);
+    fe seven = fe_zero(); seven.v[0] = 7;
+    fe y2 = fe_add(fe_mul(fe_sqr(x), x), seven);
+    fe y = fe_sqrt_candidate(y2);
+    if (!st && !fe_eq(fe_sqr(y), y2)) st = ST_THROW_INVALID_POINT;       // short.js:194-195
+    y = fe_normalize(y);
+    bool odd = tag == 3;
+    if (((y.v[0] & 1) != 0) != odd) y = fe_normalize(fe_neg(y));
+    x = fe_normalize(x);
+    store_be<8>(xy + 64 * i, x.v);
+    store_be<8>(xy + 64 * i + 32, y.v);
+  }
+  pre[i] = st;
 }
 
 __global__ void k256_selftest_fe_kernel(int op, size_t n, const u32* a, const u32* b, u32* out) {
@@ -63,18 +99,104 @@ __global__ void k256_selftest_fe_kernel(int op, size_t n, const u32* a, const u3
 }
 
 // ---------------------------------------------------------------------------
+// generic short-Weierstrass (a = -3) kernels
+template <class C>
+__global__ void __launch_bounds__(128) sw_gtab_kernel(u32* gtab) {
+  typedef SW<C> W;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)W::GWINDOWS * W::GENTRIES) return;
+  int j = (int)(t / W::GENTRIES), idx = (int)(t % W::GENTRIES);
+  W::gtab_entry(j, idx, gtab + t * 2 * W::N);
+}
+template <class C>
+__global__ void __launch_bounds__(128) sw_prep_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r,
+                                                      const uint8_t* __restrict__ s, u32* __restrict__ ws,
+                                                      u32* __restrict__ scratch) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  SW<C>::prep_thread(tid, T, N, e, r, s, ws, scratch);
+}
+template <class C>
+__global__ void __launch_bounds__(128, 2)
+sw_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __restrict__ r, const u32* __restrict__ ws,
+                 const u32* __restrict__ gtab, u32* __restrict__ qtab, const uint8_t* __restrict__ pre,
+                 uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (pre && pre[i]) { status[i] = pre[i]; return; }
+  status[i] = SW<C>::verify_item(i, N, pub, r, ws, gtab, qtab);
+}
+template <class C>
+__global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint8_t* __restrict__ in, u32 fmt,
+                                                            uint8_t* __restrict__ xy, uint8_t* __restrict__ pre) {
+  typedef SW<C> W;
+  typedef typename W::F F;
+  constexpr int NL = W::N;
+  constexpr size_t LEN = 4 * NL;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  uint8_t st = 0;
+  if (fmt == EB200_PUB_SEC1_65) {
+    const uint8_t* p = in + (1 + 2 * LEN) * i;
+    uint8_t tag = p[0];
+    if (tag != 4 && tag != 6 && tag != 7) st = ST_THROW_POINT_FORMAT;
+    else if ((tag == 6 && (p[2 * LEN] & 1)) || (tag == 7 && !(p[2 * LEN] & 1))) st = ST_THROW_ASSERT;
+    for (size_t k = 0; k < 2 * LEN; k++) xy[2 * LEN * i + k] = p[1 + k];
+  } else {
+    const uint8_t* p = in + (1 + LEN) * i;
+    uint8_t tag = p[0];
+    if (tag != 2 && tag != 3) st = ST_THROW_POINT_FORMAT;
+    typename F::fe t;
+    load_be<NL>(t.v, p + 1);
+    typename F::fe x = F::to_mont(t);
+    typename F::fe y2 = F::add(F::sub(F::mul(F::sqr(x), x), F::add(F::dbl(x), x)), C::b());
+    u32 e[NL]; F::Params::mod(e);                     // (p+1)/4: p = 3 mod 4 for p256 and p384
+    { u32 one[NL] = {1}; add_n<NL>(e, e, one); }
+    for (int k = 0; k < NL; k++) e[k] = (e[k] >> 2) | ((k + 1 < NL ? e[k + 1] : 0u) << 30);
+    typename F::fe y = F::pow(y2, e);
+    if (!st && !F::eq(F::sqr(y), y2)) st = ST_THROW_INVALID_POINT;
+    typename F::fe yp = F::from_mont(y);
+    bool odd = tag == 3;
+    if (((yp.v[0] & 1) != 0) != odd) yp = F::from_mont(F::neg(y));
+    typename F::fe xp = F::from_mont(x);
+    store_be<NL>(xy + 2 * LEN * i, xp.v);
+    store_be<NL>(xy + 2 * LEN * i + LEN, yp.v);
+  }
+  pre[i] = st;
+}
+template <class C>
+__global__ void sw_selftest_fe_kernel(int op, size_t n, const u32* a, const u32* b, u32* out) {
+  typedef typename SW<C>::F F;
+  constexpr int NL = SW<C>::N;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  typename F::fe A = F::to_mont(load_fe_n<NL>(a + NL * i)), B = F::to_mont(load_fe_n<NL>(b + NL * i)), R;
+  switch (op) {
+    case 0: R = F::mul(A, B); break;
+    case 1: R = F::sqr(A); break;
+    case 2: R = F::add(A, B); break;
+    case 3: R = F::sub(A, B); break;
+    case 4: R = F::neg(A); break;
+    case 7: R = F::inv(A); break;
+    default: R = A;
+  }
+  store_fe_n<NL>(out + NL * i, F::from_mont(R));
+}
+
+// ---------------------------------------------------------------------------
 // context
 namespace {
+constexpr int MAX_CHUNKS = 16;
 struct Ctx {
   bool ready = false;
   int device = -1;
-  cudaStream_t stream = nullptr;
-  u32* gtab_k256 = nullptr;
-  // grow-on-demand device staging for the host-pointer API
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  u32* gtab[8] = {};
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
   uint8_t* d_ws = nullptr; size_t d_ws_cap = 0;
   uint8_t* d_status = nullptr; size_t d_status_cap = 0;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k0[MAX_CHUNKS] = {}, ev_k1[MAX_CHUNKS] = {}, ev_done[MAX_CHUNKS] = {};
   eb200_timing timing = {};
   bool dev_timing_pending = false;
 };
@@ -95,38 +217,112 @@ int grow(uint8_t** p, size_t* cap, size_t need) {
   *cap = need;
   return EB200_OK;
 }
-
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-struct WsLayout { size_t ws, scratch, qtab, total; };
-WsLayout ws_layout(size_t n) {
+size_t curve_len(int curve) {
+  switch (curve) {
+    case EB200_CURVE_SECP256K1: case EB200_CURVE_P256: return 32;
+    case EB200_CURVE_P384: return 48;
+    default: return 0;
+  }
+}
+size_t pub_item_bytes(size_t len, u32 fmt) {
+  return fmt == EB200_PUB_XY ? 2 * len : fmt == EB200_PUB_SEC1_65 ? 1 + 2 * len : fmt == EB200_PUB_SEC1_33 ? 1 + len : 0;
+}
+
+// workspace: [ws words | scratch words | qtab words | decoded xy | pre-status]
+struct WsLayout { size_t ws, scratch, qtab, xy, pre, total; };
+WsLayout ws_layout(int curve, size_t n) {
+  size_t prep_words, scratch_words, qtab_words, len = curve_len(curve);
+  if (curve == EB200_CURVE_SECP256K1) { prep_words = PREP_WORDS; scratch_words = 8; qtab_words = QTAB_WORDS; }
+  else if (curve == EB200_CURVE_P256) { prep_words = SW<P256>::PREP_WORDS; scratch_words = 8; qtab_words = SW<P256>::QTAB_WORDS; }
+  else { prep_words = SW<P384>::PREP_WORDS; scratch_words = 12; qtab_words = SW<P384>::QTAB_WORDS; }
   WsLayout L;
   L.ws = 0;
-  L.scratch = align256(L.ws + (size_t)PREP_WORDS * n * 4);
-  L.qtab = align256(L.scratch + (size_t)8 * n * 4);
-  L.total = align256(L.qtab + (size_t)QTAB_WORDS * n * 4);
+  L.scratch = align256(L.ws + prep_words * n * 4);
+  L.qtab = align256(L.scratch + scratch_words * n * 4);
+  L.xy = align256(L.qtab + qtab_words * n * 4);
+  L.pre = align256(L.xy + 2 * len * n);
+  L.total = align256(L.pre + n);
   return L;
 }
 
-int launch_k256_verify(size_t n, const uint8_t* d_e, const uint8_t* d_r, const uint8_t* d_s,
-                       const uint8_t* d_pub, uint8_t* d_status, uint8_t* d_workspace,
-                       cudaStream_t st, cudaEvent_t ev_main0, cudaEvent_t ev_main1) {
+template <class C>
+int sw_ensure_table(int curve) {
+  typedef SW<C> W;
+  if (g.gtab[curve]) return EB200_OK;
+  size_t entries = (size_t)W::GWINDOWS * W::GENTRIES;
+  CK(cudaMalloc(&g.gtab[curve], entries * 2 * W::N * 4));
+  sw_gtab_kernel<C><<<(unsigned)((entries + 127) / 128), 128, 0, g.stream>>>(g.gtab[curve]);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  return EB200_OK;
+}
+int ensure_table(int curve) {
+  if (curve == EB200_CURVE_SECP256K1) {
+    if (g.gtab[curve]) return EB200_OK;
+    size_t entries = (size_t)GTAB_WINDOWS * GTAB_ENTRIES;
+    CK(cudaMalloc(&g.gtab[curve], entries * 16 * 4));
+    k256_gtab_kernel<<<(unsigned)((entries + 127) / 128), 128, 0, g.stream>>>(g.gtab[curve]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g.stream));
+    return EB200_OK;
+  }
+  if (curve == EB200_CURVE_P256) return sw_ensure_table<P256>(curve);
+  if (curve == EB200_CURVE_P384) return sw_ensure_table<P384>(curve);
+  return EB200_ERR_UNSUPPORTED;
+}
+
+// Launches decode (if needed) + prep + verify for n items on stream st.  All pointers are device pointers.
+int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, const uint8_t* d_s,
+                  const uint8_t* d_pub, u32 pub_fmt, uint8_t* d_status, uint8_t* d_workspace,
+                  cudaStream_t st, cudaEvent_t ev_main0, cudaEvent_t ev_main1, unsigned* launches) {
   if (n == 0) return EB200_OK;
-  WsLayout L = ws_layout(n);
+  WsLayout L = ws_layout(curve, n);
   u32* ws = (u32*)(d_workspace + L.ws);
   u32* scratch = (u32*)(d_workspace + L.scratch);
   u32* qtab = (u32*)(d_workspace + L.qtab);
+  const uint8_t* xy = d_pub;
+  const uint8_t* pre = nullptr;
+  unsigned nb = (unsigned)((n + 127) / 128);
   size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
   unsigned pb = (unsigned)((T + 127) / 128);
-  k256_prep_kernel<<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
-  CK(cudaGetLastError());
-  unsigned vb = (unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK);
-  if (ev_main0) CK(cudaEventRecord(ev_main0, st));
-  k256_verify_kernel<<<vb, EB_VERIFY_BLOCK, 0, st>>>(n, d_pub, d_r, ws, g.gtab_k256, qtab, d_status);
+  unsigned cnt = 0;
+  if (pub_fmt != EB200_PUB_XY) {
+    uint8_t* dxy = d_workspace + L.xy;
+    uint8_t* dpre = d_workspace + L.pre;
+    if (curve == EB200_CURVE_SECP256K1) k256_decode_pub_kernel<<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    else if (curve == EB200_CURVE_P256) sw_decode_pub_kernel<P256><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    else sw_decode_pub_kernel<P384><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    CK(cudaGetLastError());
+    xy = dxy; pre = dpre; cnt++;
+  }
+  if (curve == EB200_CURVE_SECP256K1) {
+    k256_prep_kernel<<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
+    CK(cudaGetLastError());
+    if (ev_main0) CK(cudaEventRecord(ev_main0, st));
+    unsigned vb = (unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK);
+    k256_verify_kernel<<<vb, EB_VERIFY_BLOCK, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+  } else if (curve == EB200_CURVE_P256) {
+    sw_prep_kernel<P256><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
+    CK(cudaGetLastError());
+    if (ev_main0) CK(cudaEventRecord(ev_main0, st));
+    sw_verify_kernel<P256><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+  } else {
+    sw_prep_kernel<P384><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
+    CK(cudaGetLastError());
+    if (ev_main0) CK(cudaEventRecord(ev_main0, st));
+    sw_verify_kernel<P384><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+  }
   CK(cudaGetLastError());
   if (ev_main1) CK(cudaEventRecord(ev_main1, st));
+  cnt += 2;
+  if (launches) *launches += cnt;
   return EB200_OK;
 }
+
+bool curve_ok(int curve) { return curve_len(curve) != 0; }
+bool fmt_ok(u32 fmt) { return fmt == EB200_PUB_XY || fmt == EB200_PUB_SEC1_65 || fmt == EB200_PUB_SEC1_33; }
 }  // namespace
 
 extern "C" {
@@ -155,14 +351,20 @@ int eb200_init(int device) {
   if (device < 0 || device >= cnt) return EB200_ERR_ARG;
   CK(cudaSetDevice(device));
   if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  if (!g.copy_stream) CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) if (!g.ev[i]) CK(cudaEventCreate(&g.ev[i]));
-  if (g.gtab_k256) { cudaFree(g.gtab_k256); g.gtab_k256 = nullptr; }
-  CK(cudaMalloc(&g.gtab_k256, (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 16 * 4));
-  k256_gtab_kernel<<<(unsigned)(((size_t)GTAB_WINDOWS * GTAB_ENTRIES + 127) / 128), 128, 0, g.stream>>>(g.gtab_k256);
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(g.stream));
+  for (int i = 0; i < MAX_CHUNKS; i++) {
+    if (!g.ev_in[i]) CK(cudaEventCreate(&g.ev_in[i]));
+    if (!g.ev_k0[i]) CK(cudaEventCreate(&g.ev_k0[i]));
+    if (!g.ev_k1[i]) CK(cudaEventCreate(&g.ev_k1[i]));
+    if (!g.ev_done[i]) CK(cudaEventCreate(&g.ev_done[i]));
+  }
+  for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
   g.device = device;
   g.ready = true;
+  // the headline curve's table is built eagerly; the others on first use
+  int rc = ensure_table(EB200_CURVE_SECP256K1);
+  if (rc) { g.ready = false; return rc; }
   return EB200_OK;
 }
 
@@ -170,12 +372,19 @@ int eb200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return EB200_OK;
   cudaSetDevice(g.device);
-  cudaFree(g.gtab_k256); g.gtab_k256 = nullptr;
+  for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
   cudaFree(g.d_in); g.d_in = nullptr; g.d_in_cap = 0;
   cudaFree(g.d_ws); g.d_ws = nullptr; g.d_ws_cap = 0;
   cudaFree(g.d_status); g.d_status = nullptr; g.d_status_cap = 0;
   for (int i = 0; i < 6; i++) if (g.ev[i]) { cudaEventDestroy(g.ev[i]); g.ev[i] = nullptr; }
+  for (int i = 0; i < MAX_CHUNKS; i++) {
+    if (g.ev_in[i]) { cudaEventDestroy(g.ev_in[i]); g.ev_in[i] = nullptr; }
+    if (g.ev_k0[i]) { cudaEventDestroy(g.ev_k0[i]); g.ev_k0[i] = nullptr; }
+    if (g.ev_k1[i]) { cudaEventDestroy(g.ev_k1[i]); g.ev_k1[i] = nullptr; }
+    if (g.ev_done[i]) { cudaEventDestroy(g.ev_done[i]); g.ev_done[i] = nullptr; }
+  }
   if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
+  if (g.copy_stream) { cudaStreamDestroy(g.copy_stream); g.copy_stream = nullptr; }
   g.ready = false;
   return EB200_OK;
 }
@@ -184,10 +393,11 @@ int eb200_last_timing(eb200_timing* out) {
   if (!out) return EB200_ERR_ARG;
   if (g.dev_timing_pending) {
     // device-pointer call: the caller has synchronised its stream by now
+    unsigned l = g.timing.launches;
     g.timing = eb200_timing{};
     if (cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]) != cudaSuccess) return EB200_ERR_CUDA;
     if (cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]) != cudaSuccess) return EB200_ERR_CUDA;
-    g.timing.launches = 2;
+    g.timing.launches = l;
     g.dev_timing_pending = false;
   }
   *out = g.timing;
@@ -195,101 +405,144 @@ int eb200_last_timing(eb200_timing* out) {
 }
 
 size_t eb200_ecdsa_verify_workspace_bytes(int curve, size_t n) {
-  if (curve != EB200_CURVE_SECP256K1) return 0;
-  return ws_layout(n).total;
+  if (!curve_ok(curve)) return 0;
+  return ws_layout(curve, n).total;
 }
 
 int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r,
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
-  if (pub_fmt != EB200_PUB_XY) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve) || !fmt_ok(pub_fmt)) return EB200_ERR_UNSUPPORTED;
   if (n && (!d_e || !d_r || !d_s || !d_pub || !d_status || !d_workspace)) return EB200_ERR_ARG;
+  int rc = ensure_table(curve);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;   // NULL is the CUDA default stream, as everywhere in CUDA
   // events on the caller's stream: eb200_last_timing() reports them once the stream has been synchronised
   CK(cudaEventRecord(g.ev[1], st));
-  int rc = launch_k256_verify(n, d_e, d_r, d_s, d_pub, d_status, (uint8_t*)d_workspace, st, g.ev[4], g.ev[5]);
+  unsigned launches = 0;
+  rc = launch_verify(curve, n, d_e, d_r, d_s, d_pub, pub_fmt, d_status, (uint8_t*)d_workspace, st, g.ev[4], g.ev[5], &launches);
   if (rc) return rc;
   CK(cudaEventRecord(g.ev[2], st));
+  g.timing.launches = launches;
   g.dev_timing_pending = true;
   return EB200_OK;
 }
 
+// Host-pointer call.  Large batches are cut into chunks: chunk k+1 is copied host->device on a copy
+// stream while chunk k is being verified, and results stream back as each chunk finishes.
 int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r,
                              const uint8_t* s, const uint8_t* pub, uint32_t pub_fmt,
                              uint8_t* status) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
-  if (pub_fmt != EB200_PUB_XY) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve) || !fmt_ok(pub_fmt)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   if (!e || !r || !s || !pub || !status) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
-  const size_t len = 32;
-  size_t in_bytes = n * (3 * len + 2 * len);
-  int rc;
-  if ((rc = grow(&g.d_in, &g.d_in_cap, in_bytes))) return rc;
-  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_layout(n).total))) return rc;
+  int rc = ensure_table(curve);
+  if (rc) return rc;
+  const size_t len = curve_len(curve), pb = pub_item_bytes(len, pub_fmt);
+  int chunks = 1;
+  if (n >= ((size_t)1 << 17)) chunks = 8;
+  if (n >= ((size_t)1 << 22)) chunks = MAX_CHUNKS;
+  size_t per = (n + chunks - 1) / chunks;
+  per = (per + 127) & ~(size_t)127;
+  size_t item_in = 3 * len + pb;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, align256(n * item_in) + 1024))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_layout(curve, per).total))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
   uint8_t* d_e = g.d_in;
   uint8_t* d_r = d_e + n * len;
   uint8_t* d_s = d_r + n * len;
   uint8_t* d_pub = d_s + n * len;
-  cudaStream_t st = g.stream;
-  CK(cudaEventRecord(g.ev[0], st));
-  CK(cudaMemcpyAsync(d_e, e, n * len, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_r, r, n * len, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_s, s, n * len, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_pub, pub, n * 2 * len, cudaMemcpyHostToDevice, st));
-  CK(cudaEventRecord(g.ev[1], st));
-  if ((rc = launch_k256_verify(n, d_e, d_r, d_s, d_pub, g.d_status, g.d_ws, st, g.ev[4], g.ev[5]))) return rc;
-  CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(g.ev[3], st));
-  CK(cudaStreamSynchronize(st));
+  cudaStream_t cs = g.copy_stream, ks = g.stream;
+  unsigned launches = 0;
+  CK(cudaEventRecord(g.ev[0], cs));
+  int used = 0;
+  for (int k = 0; k < chunks; k++) {
+    size_t lo = (size_t)k * per;
+    if (lo >= n) break;
+    size_t m = (lo + per <= n) ? per : n - lo;
+    used = k + 1;
+    CK(cudaMemcpyAsync(d_e + lo * len, e + lo * len, m * len, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_r + lo * len, r + lo * len, m * len, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_s + lo * len, s + lo * len, m * len, cudaMemcpyHostToDevice, cs));
+    CK(cudaMemcpyAsync(d_pub + lo * pb, pub + lo * pb, m * pb, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(g.ev_in[k], cs));
+    CK(cudaStreamWaitEvent(ks, g.ev_in[k], 0));
+    if ((rc = launch_verify(curve, m, d_e + lo * len, d_r + lo * len, d_s + lo * len, d_pub + lo * pb, pub_fmt,
+                            g.d_status + lo, g.d_ws, ks, g.ev_k0[k], g.ev_k1[k], &launches))) return rc;
+    CK(cudaEventRecord(g.ev_done[k], ks));
+  }
+  // results: one device->host copy per chunk, behind that chunk's kernels, on the copy stream
+  for (int k = 0; k < used; k++) {
+    size_t lo = (size_t)k * per;
+    size_t m = (lo + per <= n) ? per : n - lo;
+    CK(cudaStreamWaitEvent(cs, g.ev_done[k], 0));
+    CK(cudaMemcpyAsync(status + lo, g.d_status + lo, m, cudaMemcpyDeviceToHost, cs));
+  }
+  CK(cudaEventRecord(g.ev[3], cs));
+  CK(cudaStreamSynchronize(cs));
+  CK(cudaStreamSynchronize(ks));
   g.dev_timing_pending = false;
-  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
-  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
-  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
-  cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
-  g.timing.launches = 2;
+  g.timing = eb200_timing{};
+  float total = 0, t = 0;
+  cudaEventElapsedTime(&total, g.ev[0], g.ev[3]);
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev_in[used - 1]);       // all inputs resident
+  for (int k = 0; k < used; k++) {
+    cudaEventElapsedTime(&t, g.ev_k0[k], g.ev_k1[k]);
+    g.timing.main_kernel_ms += t;
+  }
+  cudaEventElapsedTime(&t, g.ev_done[used - 1], g.ev[3]);
+  g.timing.d2h_ms = t;                                                       // exposed tail copy
+  g.timing.kernel_ms = total;                                                // whole call on the GPU timeline
+  g.timing.launches = launches;
   return EB200_OK;
 }
 
 int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
+  size_t bytes = n * curve_len(curve);
   u32 *da, *db, *dout;
-  CK(cudaMalloc(&da, n * 32)); CK(cudaMalloc(&db, n * 32)); CK(cudaMalloc(&dout, n * 32));
-  CK(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
-  k256_selftest_fe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, g.stream>>>(op, n, da, db, dout);
+  CK(cudaMalloc(&da, bytes)); CK(cudaMalloc(&db, bytes)); CK(cudaMalloc(&dout, bytes));
+  CK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+  unsigned nb = (unsigned)((n + 127) / 128);
+  if (curve == EB200_CURVE_SECP256K1) k256_selftest_fe_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
+  else if (curve == EB200_CURVE_P256) sw_selftest_fe_kernel<P256><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
+  else sw_selftest_fe_kernel<P384><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
-  CK(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return EB200_OK;
 }
 
 int eb200_selftest_gtab_dims(int curve, int* windows, int* entries, int* wbits) {
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
   if (!windows || !entries || !wbits) return EB200_ERR_ARG;
-  *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W;
+  if (curve == EB200_CURVE_SECP256K1) { *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W; }
+  else if (curve == EB200_CURVE_P256) { *windows = SW<P256>::GWINDOWS; *entries = SW<P256>::GENTRIES; *wbits = SW<P256>::GW; }
+  else if (curve == EB200_CURVE_P384) { *windows = SW<P384>::GWINDOWS; *entries = SW<P384>::GENTRIES; *wbits = SW<P384>::GW; }
+  else return EB200_ERR_UNSUPPORTED;
   return EB200_OK;
 }
 
 int eb200_selftest_gtab(int curve, uint32_t* out, size_t n_words) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
-  size_t words = (size_t)GTAB_WINDOWS * GTAB_ENTRIES * 16;
+  int w, en, b;
+  int rc = eb200_selftest_gtab_dims(curve, &w, &en, &b);
+  if (rc) return rc;
+  size_t words = (size_t)w * en * 2 * (curve_len(curve) / 4);
   if (!out || n_words < words) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
-  CK(cudaMemcpy(out, g.gtab_k256, words * 4, cudaMemcpyDeviceToHost));
+  if ((rc = ensure_table(curve))) return rc;
+  CK(cudaMemcpy(out, g.gtab[curve], words * 4, cudaMemcpyDeviceToHost));
   return EB200_OK;
 }
 

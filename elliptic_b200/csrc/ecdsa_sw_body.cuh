@@ -1,0 +1,278 @@
+// ecdsa_sw_body.cuh -- batch ECDSA verify on short Weierstrass curves with a = -3 and no
+// endomorphism (p256, p384), generic over a curve-parameter struct C (sw_params_gen.inc).
+//
+// Reference path (lib/elliptic): ec/index.js:188-229 EC.verify -> short.js:443-450
+// jmulAdd -> base.js:128-253 _wnafMulAdd(1, [G, Q], [u1, u2], 2, true) with G's wnd-8 table
+// (ec/index.js:36, base.js:321) and JPoint._threeDbl (short.js:739-800); field = BN.mont(p)
+// (curves.js:75,90).  Same outputs, B200 schedule: one thread per signature; u2*Q by regular
+// signed-odd 4-bit windows over a per-item Jacobian table {1,3,..,15}Q, u1*G by GW-bit windows
+// over a fixed affine table; CIOS Montgomery field; exceptional cases in cold paths.
+#pragma once
+#include "fp_mont.cuh"
+
+namespace eb {
+
+#include "sw_params_gen.inc"
+
+template <class C>
+struct SW {
+  typedef typename C::F F;
+  typedef typename C::S S;
+  typedef typename F::fe fe;
+  static constexpr int N = C::N;
+  struct jac { fe x, y, z; };
+  struct aff { fe x, y; };
+
+  static constexpr int MBITS = C::BITS - 1;                  // bits of m = (u'-1)/2
+  static constexpr int QWINDOWS = (MBITS + 3) / 4;
+  static_assert(MBITS - 4 * (QWINDOWS - 1) <= 3, "top 4-bit digit must stay positive");
+  static constexpr int GW = C::GW;
+  static constexpr int GWINDOWS = (MBITS + GW - 1) / GW;
+  static constexpr int GENTRIES = 1 << (GW - 1);
+  static_assert(MBITS - GW * (GWINDOWS - 1) <= GW - 1, "top fixed-base digit must stay positive");
+  static constexpr int PREP_WORDS = 2 * N + 1;               // mG[N], m2[N], flags
+  static constexpr int QTAB_WORDS = 8 * 3 * N;               // 8 Jacobian entries
+  static constexpr int BATCH = 16;
+  static constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG2 = 4;
+
+  static EB_HD jac infinity() { jac r; r.x = F::one(); r.y = F::one(); r.z = F::zero(); return r; }
+  static EB_HD jac from_aff(const aff& p) { jac r; r.x = p.x; r.y = p.y; r.z = F::one(); return r; }
+
+  // dbl-2001-b (a = -3): 3M + 5S   (short.js:766-796)
+  static EB_HD jac dbl_inl(const jac& p) {
+    fe delta = F::sqr(p.z);
+    fe gamma = F::sqr(p.y);
+    fe beta = F::mul(p.x, gamma);
+    fe alpha = F::mul(F::sub(p.x, delta), F::add(p.x, delta));
+    alpha = F::add(F::dbl(alpha), alpha);
+    fe beta4 = F::dbl(F::dbl(beta));
+    jac r;
+    r.x = F::sub(F::sqr(alpha), F::dbl(beta4));
+    r.z = F::sub(F::sub(F::sqr(F::add(p.y, p.z)), gamma), delta);
+    fe g8 = F::dbl(F::dbl(F::dbl(F::sqr(gamma))));
+    r.y = F::sub(F::mul(alpha, F::sub(beta4, r.x)), g8);
+    return r;
+  }
+
+  // Jacobian + affine, all cases exact (short.js:569-603)
+  static EB_HD jac madd_inl(const jac& a, const aff& p) {
+    fe z2 = F::sqr(a.z);
+    fe u2 = F::mul(p.x, z2);
+    fe s2 = F::mul(F::mul(p.y, z2), a.z);
+    fe h = F::sub(a.x, u2);
+    fe rr = F::sub(a.y, s2);
+    fe h2 = F::sqr(h);
+    fe h3 = F::mul(h2, h);
+    fe v = F::mul(a.x, h2);
+    jac r;
+    r.x = F::sub(F::sub(F::add(F::sqr(rr), h3), v), v);
+    r.y = F::sub(F::mul(rr, F::sub(v, r.x)), F::mul(a.y, h3));
+    r.z = F::mul(a.z, h);
+    if (F::is_zero(r.z)) {
+      if (F::is_zero(a.z)) return from_aff(p);
+      if (F::is_zero(rr)) return dbl_inl(a);
+      return infinity();
+    }
+    return r;
+  }
+
+  // Jacobian + Jacobian, all cases exact (short.js:532-567)
+  static EB_HD jac add_inl(const jac& a, const jac& b) {
+    fe bz2 = F::sqr(b.z);
+    fe az2 = F::sqr(a.z);
+    fe u1 = F::mul(a.x, bz2);
+    fe u2 = F::mul(b.x, az2);
+    fe s1 = F::mul(a.y, F::mul(bz2, b.z));
+    fe s2 = F::mul(b.y, F::mul(az2, a.z));
+    fe h = F::sub(u1, u2);
+    fe rr = F::sub(s1, s2);
+    fe h2 = F::sqr(h);
+    fe h3 = F::mul(h2, h);
+    fe v = F::mul(u1, h2);
+    jac r;
+    r.x = F::sub(F::sub(F::add(F::sqr(rr), h3), v), v);
+    r.y = F::sub(F::mul(rr, F::sub(v, r.x)), F::mul(s1, h3));
+    r.z = F::mul(F::mul(a.z, b.z), h);
+    if (F::is_zero(r.z)) {
+      if (F::is_zero(a.z)) return b;
+      if (F::is_zero(b.z)) return a;
+      if (F::is_zero(rr)) return dbl_inl(a);
+      return infinity();
+    }
+    return r;
+  }
+
+#if defined(__CUDACC__)
+#define EB_SWFN static __host__ __device__ __noinline__
+#else
+#define EB_SWFN static
+#endif
+  EB_SWFN jac dbl(jac p) { return dbl_inl(p); }
+  EB_SWFN jac madd(jac a, aff p) { return madd_inl(a, p); }
+  EB_SWFN jac add(jac a, jac b) { return add_inl(a, b); }
+
+  static EB_HD aff to_aff(const jac& a) {
+    fe zi = F::inv(a.z);
+    fe zi2 = F::sqr(zi);
+    aff r;
+    r.x = F::mul(a.x, zi2);
+    r.y = F::mul(F::mul(a.y, zi2), zi);
+    return r;
+  }
+
+  // y^2 == x^3 - 3x + b  (ShortCurve.validate, short.js:206-216)
+  static EB_HD bool on_curve(const aff& p) {
+    fe x3 = F::mul(F::sqr(p.x), p.x);
+    fe t = F::sub(x3, F::add(F::dbl(p.x), p.x));
+    return F::eq(F::sqr(p.y), F::add(t, C::b()));
+  }
+
+  // ---- fixed-base table entry (j, idx) = (2 idx + 1) 2^(GW j) G, affine, Montgomery form
+  static EB_HD void gtab_entry(int j, int idx, u32* out) {
+    aff g; g.x = C::gx(); g.y = C::gy();
+    jac b = from_aff(g);
+    for (int k = 0; k < GW * j; k++) b = dbl(b);
+    aff base = to_aff(b);
+    u32 s = 2 * idx + 1;
+    jac acc = infinity();
+    for (int k = GW - 1; k >= 0; k--) {
+      acc = dbl(acc);
+      if ((s >> k) & 1) acc = madd(acc, base);
+    }
+    aff r = to_aff(acc);
+    store_fe_n<N>(out, r.x);
+    store_fe_n<N>(out + N, r.y);
+  }
+
+  // ---- prep: batched s^-1 (Montgomery trick, BATCH items/thread), u1, u2, odd-ification
+  static EB_HD void prep_thread(size_t tid, size_t T, size_t cnt_items, const uint8_t* e, const uint8_t* r,
+                                const uint8_t* s, u32* ws, u32* scratch) {
+    typedef typename S::fe sc;
+    const size_t LEN = 4 * N;
+    u32 nmod[N];
+    n_limbs(nmod);
+    sc prod = S::one();
+    u32 invalid_mask = 0;
+    int cnt = 0;
+    for (int j = 0; j < BATCH; j++) {
+      size_t i = tid + (size_t)j * T;
+      if (i >= cnt_items) break;
+      cnt = j + 1;
+      sc sv, rv;
+      load_be<N>(sv.v, s + LEN * i);
+      load_be<N>(rv.v, r + LEN * i);
+      bool ok = !is_zero_n<N>(sv.v) && !geq_n<N>(sv.v, nmod) && !is_zero_n<N>(rv.v) && !geq_n<N>(rv.v, nmod);
+      if (!ok) invalid_mask |= 1u << j;
+      sc sm = S::cmov(S::to_mont(sv), S::one(), !ok);
+      for (int w = 0; w < N; w++) scratch[(size_t)w * cnt_items + i] = prod.v[w];
+      prod = S::mul(prod, sm);
+    }
+    if (cnt == 0) return;
+    sc inv = S::inv(prod);
+    for (int j = cnt - 1; j >= 0; j--) {
+      size_t i = tid + (size_t)j * T;
+      bool ok = !((invalid_mask >> j) & 1);
+      sc sv, rv, ev, pre;
+      load_be<N>(sv.v, s + LEN * i);
+      sc sm = S::cmov(S::to_mont(sv), S::one(), !ok);
+      for (int w = 0; w < N; w++) pre.v[w] = scratch[(size_t)w * cnt_items + i];
+      sc sinv = S::mul(inv, pre);
+      inv = S::mul(inv, sm);
+      u32 flags = ok ? 0 : FL_INVALID;
+      load_be<N>(rv.v, r + LEN * i);
+      load_be<N>(ev.v, e + LEN * i);
+      sc u1 = S::mul(ev, sinv);     // plain e * Montgomery s^-1 -> plain   (ec/index.js:206)
+      sc u2 = S::mul(rv, sinv);     //                                        (ec/index.js:207)
+      if ((u1.v[0] & 1) == 0) { sub_n<N>(u1.v, nmod, u1.v); flags |= FL_NEGG; }
+      if ((u2.v[0] & 1) == 0) { sub_n<N>(u2.v, nmod, u2.v); flags |= FL_NEG2; }
+      for (int w = 0; w < N; w++) {
+        u32 h1 = (w < N - 1) ? u1.v[w + 1] : 0, h2 = (w < N - 1) ? u2.v[w + 1] : 0;
+        ws[(size_t)w * cnt_items + i] = (u1.v[w] >> 1) | (h1 << 31);
+        ws[(size_t)(N + w) * cnt_items + i] = (u2.v[w] >> 1) | (h2 << 31);
+      }
+      ws[(size_t)(2 * N) * cnt_items + i] = flags;
+    }
+  }
+
+  static EB_HD void n_limbs(u32* r) { S::Params::mod(r); }
+
+  static EB_HD u32 extract(const u32* ws, size_t cnt_items, size_t i, int base_word, int pos, int width) {
+    int wi = pos >> 5;
+    u32 lo = ws[(size_t)(base_word + wi) * cnt_items + i];
+    u32 hi = (wi + 1 < N) ? ws[(size_t)(base_word + wi + 1) * cnt_items + i] : 0u;
+    u64 both = ((u64)hi << 32) | lo;
+    return (u32)(both >> (pos & 31)) & ((1u << width) - 1);
+  }
+
+  // ---- main: one signature
+  static EB_HD uint8_t verify_item(size_t i, size_t cnt_items, const uint8_t* pub, const uint8_t* r,
+                                   const u32* ws, const u32* gtab, u32* qtab) {
+    const size_t LEN = 4 * N;
+    u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
+    if (flags & FL_INVALID) return 0;   // ST_FALSE
+    aff Q;
+    {
+      fe t;
+      load_be<N>(t.v, pub + 2 * LEN * i);       Q.x = F::to_mont(t);
+      load_be<N>(t.v, pub + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
+    }
+    if (!on_curve(Q)) return 4;          // ST_NEEDS_HOST (un-validated off-curve key)
+
+    u32* tab = qtab + (size_t)i * QTAB_WORDS;
+    {
+      jac P = from_aff(Q);
+      jac D = dbl(P);
+      for (int k = 0; k < 8; k++) {
+        store_fe_n<N>(tab + 3 * N * k, P.x);
+        store_fe_n<N>(tab + 3 * N * k + N, P.y);
+        store_fe_n<N>(tab + 3 * N * k + 2 * N, P.z);
+        if (k < 7) P = add(P, D);
+      }
+    }
+    jac acc = infinity();
+    for (int w = QWINDOWS - 1; w >= 0; w--) {
+      if (w != QWINDOWS - 1)
+        for (int d = 0; d < 4; d++) acc = dbl(acc);
+      u32 nib = extract(ws, cnt_items, i, N, 4 * w, 4);
+      bool dneg = (w != QWINDOWS - 1) && (nib < 8);
+      u32 idx = (w == QWINDOWS - 1) ? (nib & 7) : (dneg ? 7 - nib : nib - 8);
+      bool neg = dneg != ((flags & FL_NEG2) != 0);
+      jac P;
+      P.x = load_fe_n<N>(tab + 3 * N * idx);
+      P.y = load_fe_n<N>(tab + 3 * N * idx + N);
+      P.z = load_fe_n<N>(tab + 3 * N * idx + 2 * N);
+      P.y = F::cmov(P.y, F::neg(P.y), neg);
+      if (w == QWINDOWS - 1) acc = P;
+      else acc = add(acc, P);
+    }
+    for (int j = 0; j < GWINDOWS; j++) {
+      u32 chunk = extract(ws, cnt_items, i, 0, GW * j, GW);
+      const u32 half = 1u << (GW - 1);
+      bool dneg = (j != GWINDOWS - 1) && (chunk < half);
+      u32 idx = (j == GWINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
+      bool neg = dneg != ((flags & FL_NEGG) != 0);
+      const u32* ent = gtab + ((size_t)j * GENTRIES + idx) * 2 * N;
+      aff P;
+      P.x = load_fe_n<N>(ent);
+      P.y = load_fe_n<N>(ent + N);
+      P.y = F::cmov(P.y, F::neg(P.y), neg);
+      acc = madd(acc, P);
+    }
+    // accept iff R != O and x(R) == r (mod n)  (ec/index.js:222-228, eqXToP short.js:908-925)
+    if (F::is_zero(acc.z)) return 0;
+    fe z2 = F::sqr(acc.z);
+    fe rp;
+    load_be<N>(rp.v, r + LEN * i);
+    if (F::eq(acc.x, F::mul(F::to_mont(rp), z2))) return 1;
+    u32 pmn[N]; C::p_minus_n(pmn);
+    if (!geq_n<N>(rp.v, pmn)) {
+      u32 nmod[N]; n_limbs(nmod);
+      fe rn;
+      add_n<N>(rn.v, rp.v, nmod);
+      if (F::eq(acc.x, F::mul(F::to_mont(rn), z2))) return 1;
+    }
+    return 0;
+  }
+};
+
+}  // namespace eb

@@ -15,8 +15,16 @@ import numpy as np
 from . import _native as nat
 
 _CURVES = {
+    # name -> C-ABI id, byte length of a field element, group order n, field prime p (curves.js:43-206)
     "secp256k1": dict(id=nat.CURVE_SECP256K1, len=32,
-                      n=0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141),
+                      n=0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
+                      p=2**256 - 2**32 - 977),
+    "p256": dict(id=nat.CURVE_P256, len=32,
+                 n=0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
+                 p=2**256 - 2**224 + 2**192 + 2**96 - 1),
+    "p384": dict(id=nat.CURVE_P384, len=48,
+                 n=0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
+                 p=2**384 - 2**128 - 2**96 + 2**32 - 1),
 }
 
 
@@ -192,9 +200,8 @@ class EC:
             # toRed reduces oversize coordinates mod p (short.js:258-268); the engine
             # does that for anything that fits the wire width, wider values here.
             if x >> (8 * ln) or y >> (8 * ln):
-                p = 2**256 - 2**32 - 977
-                x %= p
-                y %= p
+                x %= self._c["p"]
+                y %= self._c["p"]
             return nat.PUB_XY, x.to_bytes(ln, "big") + y.to_bytes(ln, "big")
         b = _to_array(key, enc)
         if len(b) and b[0] in (4, 6, 7) and len(b) - 1 == 2 * ln:
@@ -216,6 +223,8 @@ class EC:
         pub = np.ascontiguousarray(pub, dtype=np.uint8)
         n = e.shape[0]
         assert e.shape == (n, self._len) and r.shape == e.shape and s.shape == e.shape
+        pb = {nat.PUB_XY: 2 * self._len, nat.PUB_SEC1_65: 1 + 2 * self._len, nat.PUB_SEC1_33: 1 + self._len}[pub_fmt]
+        assert pub.shape == (n, pb), (pub.shape, pb)
         status = np.empty(n, dtype=np.uint8)
         nat.check(lib.eb200_ecdsa_verify_batch(
             self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data, pub.ctypes.data,
@@ -231,24 +240,29 @@ class EC:
         e = np.zeros((n, ln), np.uint8)
         r = np.zeros((n, ln), np.uint8)
         s = np.zeros((n, ln), np.uint8)
-        pub = np.zeros((n, 2 * ln), np.uint8)
+        groups = {}          # pub format -> (item indices, key bytes)
         early = {}
         for i in range(n):
             ev = self._truncate_to_n(msgs[i], msg_bit_length)
             fmt, pb = self._public(keys[i], enc)
-            if fmt != nat.PUB_XY:
-                raise EllipticError("compressed keys: use verify_batch_packed with PUB_SEC1_33")
             rv, sv = self._signature(sigs[i])
             if rv < 1 or rv >= self.n or sv < 1 or sv >= self.n:
-                early[i] = nat.ST_FALSE       # ec/index.js:199-202
+                early[i] = nat.ST_FALSE       # ec/index.js:199-202 (after the key import, which may throw)
                 rv = sv = 0
             e[i] = np.frombuffer(ev.to_bytes(ln, "big"), np.uint8)
             r[i] = np.frombuffer(rv.to_bytes(ln, "big"), np.uint8)
             s[i] = np.frombuffer(sv.to_bytes(ln, "big"), np.uint8)
-            pub[i] = np.frombuffer(pb, np.uint8)
-        st = self.verify_batch_packed(e, r, s, pub)
+            g = groups.setdefault(fmt, ([], []))
+            g[0].append(i)
+            g[1].append(pb)
+        st = np.zeros(n, np.uint8)
+        for fmt, (idx, pbs) in groups.items():
+            idx = np.asarray(idx)
+            pub = np.frombuffer(b"".join(pbs), np.uint8).reshape(len(pbs), -1)
+            st[idx] = self.verify_batch_packed(e[idx], r[idx], s[idx], pub, fmt)
         for i, v in early.items():
-            st[i] = v
+            if st[i] in (nat.ST_TRUE, nat.ST_FALSE, nat.ST_NEEDS_HOST):
+                st[i] = v
         return st
 
     def verify(self, msg, signature, key, enc=None, options=None):

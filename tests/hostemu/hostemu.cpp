@@ -69,3 +69,37 @@ void he_verify(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, c
   for (size_t i = 0; i < N; i++) status[i] = verify_item(i, N, pub, r, ws.data(), gtab, qtab.data());
 }
 }
+
+// ---------------------------------------------------------------------------
+// generic short-Weierstrass path (p256 / p384) through the same bodies
+#include "../../elliptic_b200/csrc/ecdsa_sw_body.cuh"
+template <class C>
+static void sw_verify_host(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
+  typedef SW<C> W;
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)W::GWINDOWS * W::GENTRIES * 2 * W::N);
+    typename W::aff g; g.x = C::gx(); g.y = C::gy();
+    typename W::jac base = W::from_aff(g);
+    for (int j = 0; j < W::GWINDOWS; j++) {
+      typename W::aff b = W::to_aff(base);
+      typename W::jac d = W::dbl(W::from_aff(b));
+      typename W::jac acc = W::from_aff(b);
+      for (int i = 0; i < W::GENTRIES; i++) {
+        typename W::aff a = W::to_aff(acc);
+        store_fe_n<W::N>(&gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N], a.x);
+        store_fe_n<W::N>(&gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N + W::N], a.y);
+        acc = W::add(acc, d);
+      }
+      for (int k = 0; k < W::GW; k++) base = W::dbl(base);
+    }
+  }
+  std::vector<u32> ws((size_t)W::PREP_WORDS * N), scratch((size_t)W::N * N), qtab((size_t)W::QTAB_WORDS * N);
+  size_t T = (N + W::BATCH - 1) / W::BATCH;
+  for (size_t t = 0; t < T; t++) W::prep_thread(t, T, N, e, r, s, ws.data(), scratch.data());
+  for (size_t i = 0; i < N; i++) status[i] = W::verify_item(i, N, pub, r, ws.data(), gtab.data(), qtab.data());
+}
+extern "C" void he_sw_verify(int curve, size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
+  if (curve == 2) sw_verify_host<P256>(N, e, r, s, pub, status);
+  else sw_verify_host<P384>(N, e, r, s, pub, status);
+}

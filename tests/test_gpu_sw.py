@@ -1,0 +1,163 @@
+"""GPU parity tests: p256 / p384 ECDSA verify (generic Montgomery path) and SEC1 key decoding."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+KATS = json.load(open(os.path.join(G, "ecdsa_kats.json")))
+CURVES = {"p256": (2, 32), "p384": (3, 48)}
+
+
+def limbs(vals, n):
+    a = np.zeros((len(vals), n), np.uint32)
+    for i, v in enumerate(vals):
+        for k in range(n):
+            a[i, k] = (v >> (32 * k)) & 0xFFFFFFFF
+    return a
+
+
+def ints(a):
+    return [sum(int(a[i, k]) << (32 * k) for k in range(a.shape[1])) for i in range(a.shape[0])]
+
+
+@pytest.mark.parametrize("name", ["p256", "p384"])
+def test_montgomery_field_bit_exact(native, name):
+    from elliptic_b200 import _native as nat
+    from oracle.ref_py import curves
+    cid, ln = CURVES[name]
+    p = curves.get(name).curve.p
+    nl = ln // 4
+    rnd = random.Random(3)
+    edge = [0, 1, 2, p - 1, p - 2, (1 << (8 * ln)) - 1, p, p + 1, 1 << (8 * ln - 1), (1 << 32) - 1, 1 << 32]
+    a = edge + [rnd.randrange(1 << (8 * ln)) for _ in range(1500)]
+    b = [a[(7 * i + 3) % len(a)] for i in range(len(a))]
+    a += [x for x in edge for _ in edge]
+    b += [y for _ in edge for y in edge]
+    A, B = limbs(a, nl), limbs(b, nl)
+    for op, fn in ((0, lambda x, y: x * y), (1, lambda x, y: x * x), (2, lambda x, y: x + y), (3, lambda x, y: x - y),
+                   (4, lambda x, y: -x)):
+        out = np.zeros_like(A)
+        nat.check(native.eb200_selftest_fe(cid, op, len(a), A.ctypes.data, B.ctypes.data, out.ctypes.data))
+        for x, y, g in zip(a, b, ints(out)):
+            assert g == fn(x, y) % p, (name, op, hex(x), hex(y))
+    out = np.zeros_like(A[:48])
+    nat.check(native.eb200_selftest_fe(cid, 7, 48, A.ctypes.data, B.ctypes.data, out.ctypes.data))
+    for x, g in zip(a[:48], ints(out)):
+        assert g == pow(x % p, p - 2, p)
+
+
+@pytest.mark.parametrize("name", ["p256", "p384"])
+def test_fixed_base_table(native, name):
+    from elliptic_b200 import _native as nat
+    from oracle.ref_py.ec import EC
+    cid, ln = CURVES[name]
+    ec = EC(name)
+    p, n, nl = ec.curve.p, ec.n, ln // 4
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    nat.check(native.eb200_selftest_gtab_dims(cid, ctypes.byref(W), ctypes.byref(E), ctypes.byref(B)))
+    W, E, B = W.value, E.value, B.value
+    tab = np.zeros(W * E * 2 * nl, np.uint32)
+    nat.check(native.eb200_selftest_gtab(cid, tab.ctypes.data, tab.size))
+    tab = tab.reshape(W, E, 2, nl)
+    R = 1 << (8 * ln)
+    rnd = random.Random(6)
+    for j, i in [(0, 0), (0, E - 1), (W - 1, 0), (W - 1, E - 1)] + [(rnd.randrange(W), rnd.randrange(E)) for _ in range(30)]:
+        pt = ec.g.mul(((2 * i + 1) << (B * j)) % n)
+        x, y = ints(tab[j, i])
+        assert (x, y) == (pt.x * R % p, pt.y * R % p), (name, j, i)     # Montgomery form
+
+
+@pytest.mark.parametrize("name", ["p256", "p384"])
+def test_verify_parity(native, name):
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    from sw_items import sw_edge_items, sw_expected
+    cid, ln = CURVES[name]
+    ec = EC(name)
+    items = sw_edge_items(ec, ln, seed=11, count=200)
+    pack = lambda k: np.frombuffer(b"".join(it[k].to_bytes(ln, "big") for it in items), np.uint8).reshape(-1, ln)
+    st = GpuEC(name).verify_batch_packed(pack(0), pack(1), pack(2), np.concatenate([pack(3), pack(4)], axis=1))
+    exp = [sw_expected(ec, ln, it) for it in items]
+    bad = [(i, int(st[i]), exp[i]) for i in range(len(items)) if int(st[i]) != exp[i]]
+    assert not bad, bad[:10]
+    assert {0, 1, 4} <= set(exp)
+
+
+def test_reference_maxwell_vectors_on_gpu(native):
+    """test/ecdsa-test.js:352-451 through the single-item API (DER sig, SEC1 key, hex)."""
+    from elliptic_b200.ec import EC as GpuEC
+    for v in KATS["maxwell"]:
+        assert GpuEC(v["curve"]).verify(v["msg"], v["sig"], v["pub"], "hex") is v["result"], v
+
+
+def test_reference_rfc6979_vectors_verify_on_gpu(native):
+    """test/ecdsa-test.js:135-350 (p256, p384): the published (r, s) must verify."""
+    from elliptic_b200.ec import EC as GpuEC
+    hs = {"sha1": hashlib.sha1, "sha224": hashlib.sha224, "sha256": hashlib.sha256, "sha384": hashlib.sha384, "sha512": hashlib.sha512}
+    seen = 0
+    for blk in KATS["rfc6979"]:
+        if blk["curve"] not in ("p256", "p384"):
+            continue
+        gec = GpuEC(blk["curve"])
+        for c in blk["cases"]:
+            dg = hs[c["hash"]](c["message"].encode()).digest()
+            assert gec.verify(dg, {"r": c["r"], "s": c["s"]}, {"x": blk["x"], "y": blk["y"]}) is True
+            bad = bytearray(dg); bad[0] ^= 1
+            assert gec.verify(bytes(bad), {"r": c["r"], "s": c["s"]}, {"x": blk["x"], "y": blk["y"]}) is False
+            seen += 1
+    assert seen >= 6
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "p256", "p384"])
+def test_sec1_key_formats_on_gpu(native, name):
+    """Compressed / hybrid / uncompressed keys decoded on the GPU (base.js:270-292, short.js:187-204),
+    including x with no square root (-> the reference throws 'invalid point')."""
+    from elliptic_b200 import _native as nat
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    from oracle.ref_py.bn import RefError
+    ec, gec = EC(name), GpuEC(name)
+    ln = (ec.curve.p.bit_length() + 7) // 8
+    rnd = random.Random(8)
+    e, r, s, comp, unc, exp_c, exp_u = [], [], [], [], [], [], []
+    for t in range(96):
+        d = rnd.randrange(1, ec.n)
+        Q = ec.g.mul(d)
+        m = rnd.randrange(1 << (8 * ln - 1))
+        sig = ec.sign(m.to_bytes(ln, "big"), d)
+        c = bytearray(Q.encode(True))
+        u = bytearray(Q.encode())
+        kind = t % 8
+        if kind == 1: c[0] ^= 1                     # wrong parity -> valid point, other key -> false
+        if kind == 2: c[0] = 5; u[0] = 5            # unknown prefix
+        if kind == 3: u[0] = 6 + (Q.y & 1)          # correct hybrid
+        if kind == 4: u[0] = 7 - (Q.y & 1)          # hybrid parity assertion fails
+        if kind == 5:                                # x without a square root
+            x = Q.x
+            while True:
+                x = (x + 1) % ec.curve.p
+                try:
+                    ec.curve.point_from_x(x, False)
+                except RefError:
+                    break
+            c[1:] = x.to_bytes(ln, "big")
+        for buf, exp in ((c, exp_c), (u, exp_u)):
+            try:
+                exp.append(int(ec.verify(m.to_bytes(ln, "big"), sig, bytes(buf))))
+            except RefError as ex:
+                exp.append({"invalid point": 2, "Assertion failed": 5, "Unknown point format": 6}[ex.args[0]])
+        e.append(m.to_bytes(ln, "big")); r.append(sig.r.to_bytes(ln, "big")); s.append(sig.s.to_bytes(ln, "big"))
+        comp.append(bytes(c)); unc.append(bytes(u))
+    arr = lambda lst: np.frombuffer(b"".join(lst), np.uint8).reshape(len(lst), -1)
+    st_c = gec.verify_batch_packed(arr(e), arr(r), arr(s), arr(comp), nat.PUB_SEC1_33)
+    st_u = gec.verify_batch_packed(arr(e), arr(r), arr(s), arr(unc), nat.PUB_SEC1_65)
+    assert [int(v) for v in st_c] == exp_c
+    assert [int(v) for v in st_u] == exp_u
+    assert {1, 0, 2, 6} <= set(exp_c) and {1, 5, 6} <= set(exp_u)

@@ -21,7 +21,7 @@ def he():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libhostemu.so")
     src = os.path.join(ROOT, "tests", "hostemu", "hostemu.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, src], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-DEB_GW=8", "-DEB_SW_GW=6", "-shared", "-fPIC", "-o", lib, src], check=True)
     return ctypes.CDLL(lib)
 
 
@@ -78,3 +78,17 @@ def test_verify_pipeline_against_oracle(he):
     st = (ctypes.c_uint8 * n)()
     he.he_verify(ctypes.c_size_t(n), col(0), col(1), col(2), pub, gtab.ctypes.data_as(ctypes.c_void_p), st)
     assert [int(v) for v in st] == [_expected(ec, it) for it in items]
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+def test_sw_verify_pipeline_against_oracle(he, name, cid, ln):
+    from oracle.ref_py.ec import EC
+    from sw_items import sw_edge_items, sw_expected
+    ec = EC(name)
+    items = sw_edge_items(ec, ln, seed=21, count=30)
+    n = len(items)
+    col = lambda k: b"".join(it[k].to_bytes(ln, "big") for it in items)
+    pub = b"".join(it[3].to_bytes(ln, "big") + it[4].to_bytes(ln, "big") for it in items)
+    st = (ctypes.c_uint8 * n)()
+    he.he_sw_verify(cid, ctypes.c_size_t(n), col(0), col(1), col(2), pub, st)
+    assert [int(v) for v in st] == [sw_expected(ec, ln, it) for it in items]
