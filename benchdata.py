@@ -37,58 +37,78 @@ def _batch_inv(vals, m):
     return out
 
 
-def _jac_dbl(X, Y, Z):
+CURVES = {
+    # name: (p, n, a, Gx, Gy, byte length)   -- public SECG / NIST parameters
+    "secp256k1": (P, N, 0, GX, GY, 32),
+    "p256": (2**256 - 2**224 + 2**192 + 2**96 - 1,
+             0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551, -3,
+             0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+             0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5, 32),
+    "p384": (2**384 - 2**128 - 2**96 + 2**32 - 1,
+             0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973, -3,
+             0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
+             0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F, 48),
+}
+
+
+def _jac_dbl(X, Y, Z, P=P, a=0):
     if Y == 0 or Z == 0:
         return 1, 1, 0
     A = X * X % P; B = Y * Y % P; C = B * B % P
     D = 2 * ((X + B) * (X + B) - A - C) % P
-    E = 3 * A % P
+    E = (3 * A + a * pow(Z, 4, P)) % P
     X3 = (E * E - 2 * D) % P
     return X3, (E * (D - X3) - 8 * C) % P, 2 * Y * Z % P
 
 
-def _jac_madd(X1, Y1, Z1, x2, y2):
+def _jac_madd(X1, Y1, Z1, x2, y2, P=P, a=0):
     if Z1 == 0:
         return x2, y2, 1
     Z2 = Z1 * Z1 % P
     U2 = x2 * Z2 % P; S2 = y2 * Z2 * Z1 % P
     H = (U2 - X1) % P; R = (S2 - Y1) % P
     if H == 0:
-        return _jac_dbl(X1, Y1, Z1) if R == 0 else (1, 1, 0)
+        return _jac_dbl(X1, Y1, Z1, P, a) if R == 0 else (1, 1, 0)
     H2 = H * H % P; H3 = H2 * H % P; V = X1 * H2 % P
     X3 = (R * R - H3 - 2 * V) % P
     return X3, (R * (V - X3) - Y1 * H3) % P, Z1 * H % P
 
 
-def scalar_mul_g(k):
+def scalar_mul_g(k, curve="secp256k1"):
+    P, _, a, GX, GY, _ = CURVES[curve]
     X, Y, Z = 1, 1, 0
     for i in range(k.bit_length() - 1, -1, -1):
-        X, Y, Z = _jac_dbl(X, Y, Z)
+        X, Y, Z = _jac_dbl(X, Y, Z, P, a)
         if (k >> i) & 1:
-            X, Y, Z = _jac_madd(X, Y, Z, GX, GY)
+            X, Y, Z = _jac_madd(X, Y, Z, GX, GY, P, a)
     zi = pow(Z, -1, P)
     return X * zi * zi % P, Y * zi * zi * zi % P
 
 
 def gen_secp256k1_verify(n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64, cache_dir=None):
-    """Returns dict of uint8 arrays e,r,s (n,32), pub (n,64) and expected (n,)."""
+    return gen_ecdsa_verify("secp256k1", n_items, seed, n_keys, corrupt_every, cache_dir)
+
+
+def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64, cache_dir=None):
+    """Returns dict of uint8 arrays e,r,s (n,len), pub (n,2*len) and expected (n,)."""
+    P, N, _a, GX, GY, LEN = CURVES[curve]
     n_keys = min(n_keys, n_items)
     per_key = (n_items + n_keys - 1) // n_keys
     if cache_dir:
-        path = os.path.join(cache_dir, "k256_%x_%d_%d_%d.npz" % (seed, n_items, n_keys, corrupt_every))
+        path = os.path.join(cache_dir, "%s_%x_%d_%d_%d.npz" % (curve, seed, n_items, n_keys, corrupt_every))
         if os.path.exists(path):
             z = np.load(path)
             return {k: z[k] for k in z.files}
     d = [_stream(seed, b"key", j) % (N - 1) + 1 for j in range(n_keys)]
     k = [_stream(seed, b"nonce", j) % (N - (per_key + 2)) + 1 for j in range(n_keys)]
-    Q = [scalar_mul_g(x) for x in d]
-    R = [scalar_mul_g(x) for x in k]
-    e_out = np.zeros((n_items, 32), np.uint8)
-    r_out = np.zeros((n_items, 32), np.uint8)
-    s_out = np.zeros((n_items, 32), np.uint8)
-    pub_out = np.zeros((n_items, 64), np.uint8)
+    Q = [scalar_mul_g(x, curve) for x in d]
+    R = [scalar_mul_g(x, curve) for x in k]
+    e_out = np.zeros((n_items, LEN), np.uint8)
+    r_out = np.zeros((n_items, LEN), np.uint8)
+    s_out = np.zeros((n_items, LEN), np.uint8)
+    pub_out = np.zeros((n_items, 2 * LEN), np.uint8)
     expected = np.ones(n_items, np.uint8)
-    pubs = [x.to_bytes(32, "big") + y.to_bytes(32, "big") for x, y in Q]
+    pubs = [x.to_bytes(LEN, "big") + y.to_bytes(LEN, "big") for x, y in Q]
     for m in range(per_key):
         kinv = _batch_inv(k, N)
         for j in range(n_keys):
@@ -96,13 +116,15 @@ def gen_secp256k1_verify(n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64
             if i >= n_items:
                 continue
             e = _stream(seed, b"msg", i)
+            if LEN > 32:
+                e = (e << (8 * (LEN - 32))) | (_stream(seed, b"msg2", i) >> (8 * (64 - LEN)))
             r = R[j][0] % N
             s = kinv[j] * (e + r * d[j]) % N
             if r == 0 or s == 0:         # astronomically unlikely; keep the item invalid
                 expected[i] = 0
             if corrupt_every and i % corrupt_every == corrupt_every - 1:
                 c = _stream(seed, b"corrupt", i)
-                which, bit = c % 3, (c >> 8) % 256
+                which, bit = c % 3, (c >> 8) % (8 * LEN - 1)
                 if which == 0:
                     e ^= 1 << bit
                 elif which == 1:
@@ -110,9 +132,9 @@ def gen_secp256k1_verify(n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64
                 else:
                     s ^= 1 << bit
                 expected[i] = 0
-            e_out[i] = np.frombuffer(e.to_bytes(32, "big"), np.uint8)
-            r_out[i] = np.frombuffer(r.to_bytes(32, "big"), np.uint8)
-            s_out[i] = np.frombuffer(s.to_bytes(32, "big"), np.uint8)
+            e_out[i] = np.frombuffer(e.to_bytes(LEN, "big"), np.uint8)
+            r_out[i] = np.frombuffer(r.to_bytes(LEN, "big"), np.uint8)
+            s_out[i] = np.frombuffer(s.to_bytes(LEN, "big"), np.uint8)
             pub_out[i] = np.frombuffer(pubs[j], np.uint8)
         if m + 1 < per_key:
             # R_j += G (affine, batched inversion); k_j += 1
@@ -138,3 +160,84 @@ if __name__ == "__main__":
     t = time.time()
     dset = gen_secp256k1_verify(n)
     print("generated", n, "in %.1fs" % (time.time() - t), "valid", int(dset["expected"].sum()))
+
+
+# ---------------------------------------------------------------------------------------------
+# ed25519 EdDSA verify -- R,S,A (wire format) + h = SHA512(R||A||M) mod n.
+N_ED = 0x1000000000000000000000000000000014DEF9DEA2F79CD65812631A5CF5D3ED
+
+
+def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, cache_dir=None):
+    """Signatures are produced with libsodium (PyNaCl) -- a generator, not the code under test.
+    1/64 items are forged the way test/ed25519-test.js:75-77 does (last message byte + 1)."""
+    import nacl.signing
+    if cache_dir:
+        path = os.path.join(cache_dir, "ed25519_%x_%d_%d_%d.npz" % (seed, n_items, n_keys, corrupt_every))
+        if os.path.exists(path):
+            z = np.load(path)
+            return {k: z[k] for k in z.files}
+    n_keys = min(n_keys, n_items)
+    keys = [nacl.signing.SigningKey(hashlib.sha256(b"eb200/%08x/edkey/%d" % (seed, j)).digest()) for j in range(n_keys)]
+    pubs = [bytes(k.verify_key) for k in keys]
+    R = np.zeros((n_items, 32), np.uint8)
+    S = np.zeros((n_items, 32), np.uint8)
+    A = np.zeros((n_items, 32), np.uint8)
+    H = np.zeros((n_items, 32), np.uint8)
+    expected = np.ones(n_items, np.uint8)
+    for i in range(n_items):
+        j = i % n_keys
+        msg = hashlib.sha256(b"eb200/%08x/edmsg/%d" % (seed, i)).digest()
+        sig = keys[j].sign(msg).signature
+        if corrupt_every and i % corrupt_every == corrupt_every - 1:
+            msg = msg[:-1] + bytes([(msg[-1] + 1) & 255])
+            expected[i] = 0
+        h = int.from_bytes(hashlib.sha512(sig[:32] + pubs[j] + msg).digest(), "little") % N_ED
+        R[i] = np.frombuffer(sig[:32], np.uint8)
+        S[i] = np.frombuffer(sig[32:], np.uint8)
+        A[i] = np.frombuffer(pubs[j], np.uint8)
+        H[i] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
+    out = dict(R=R, S=S, A=A, h=H, expected=expected)
+    if cache_dir:
+        os.makedirs(cache_dir, exist_ok=True)
+        np.savez(path, **out)
+    return out
+
+
+# BASELINE.md config 4: curve25519 ECDH derive -- priv, pubx big-endian; 1/256 twist points.
+def gen_x25519_derive(n_items, seed=0xE1110004, n_pubs=4096, twist_every=256, cache_dir=None):
+    import nacl.bindings
+    P25 = 2**255 - 19
+    if cache_dir:
+        path = os.path.join(cache_dir, "x25519_%x_%d_%d_%d.npz" % (seed, n_items, n_pubs, twist_every))
+        if os.path.exists(path):
+            z = np.load(path)
+            return {k: z[k] for k in z.files}
+    n_pubs = min(n_pubs, n_items)
+    pubs = []
+    for j in range(n_pubs):
+        sk = hashlib.sha256(b"eb200/%08x/xpub/%d" % (seed, j)).digest()
+        pubs.append(int.from_bytes(nacl.bindings.crypto_scalarmult_base(sk), "little"))
+    twists = []
+    t = 2
+    while len(twists) < 16:
+        rhs = (t * t * t + 486662 * t * t + t) % P25
+        if pow(rhs, (P25 - 1) // 2, P25) == P25 - 1:
+            twists.append(t)
+        t += 1
+    priv = np.zeros((n_items, 32), np.uint8)
+    pubx = np.zeros((n_items, 32), np.uint8)
+    expected = np.ones(n_items, np.uint8)
+    for i in range(n_items):
+        k = _stream(seed, b"xpriv", i) % (N_ED - 1) + 1
+        if twist_every and i % twist_every == twist_every - 1:
+            x = twists[(i // twist_every) % len(twists)]
+            expected[i] = 5          # the reference throws (bn.js sqrt assertion inside validate)
+        else:
+            x = pubs[i % n_pubs]
+        priv[i] = np.frombuffer(k.to_bytes(32, "big"), np.uint8)
+        pubx[i] = np.frombuffer(x.to_bytes(32, "big"), np.uint8)
+    out = dict(priv=priv, pubx=pubx, expected=expected)
+    if cache_dir:
+        os.makedirs(cache_dir, exist_ok=True)
+        np.savez(path, **out)
+    return out

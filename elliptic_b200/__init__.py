@@ -5,6 +5,7 @@ N-API shim a maintainer would add is in binding/ and INTEGRATION.md) mirroring
 `require('elliptic')` for the accelerated path (lib/elliptic.js:5-13).
 """
 from .ec import EC as ec  # noqa: F401,N813  (reference export name)
+from .eddsa import EDDSA as eddsa  # noqa: F401,N813
 from . import _native  # noqa: F401
 
 version = "0.1.0"

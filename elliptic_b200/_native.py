@@ -20,6 +20,8 @@ EXPORTS = [
     "eb200_init", "eb200_shutdown", "eb200_strerror", "eb200_last_error", "eb200_last_timing",
     "eb200_ecdsa_verify_batch", "eb200_ecdsa_verify_workspace_bytes", "eb200_ecdsa_verify_batch_dev",
     "eb200_selftest_fe", "eb200_selftest_gtab", "eb200_selftest_gtab_dims",
+    "eb200_eddsa_verify_batch", "eb200_eddsa_verify_workspace_bytes", "eb200_eddsa_verify_batch_dev",
+    "eb200_x25519_derive_batch", "eb200_x25519_derive_batch_dev",
 ]
 
 
@@ -55,6 +57,13 @@ def load():
     lib.eb200_ecdsa_verify_workspace_bytes.restype = c.c_size_t
     lib.eb200_ecdsa_verify_workspace_bytes.argtypes = [c.c_int, c.c_size_t]
     lib.eb200_ecdsa_verify_batch_dev.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4 + [c.c_uint32] + [c.c_void_p] * 3
+    lib.eb200_eddsa_verify_batch.argtypes = [c.c_size_t] + [c.c_void_p] * 5
+    lib.eb200_eddsa_verify_workspace_bytes.restype = c.c_size_t
+    lib.eb200_eddsa_verify_workspace_bytes.argtypes = [c.c_size_t]
+    lib.eb200_eddsa_verify_batch_dev.argtypes = [c.c_size_t] + [c.c_void_p] * 7
+    lib.eb200_x25519_derive_batch.argtypes = [c.c_size_t] + [c.c_void_p] * 4
+    lib.eb200_x25519_derive_batch_dev.argtypes = [c.c_size_t] + [c.c_void_p] * 5
+    lib.eb200_selftest_gtab_dims.argtypes = [c.c_int] + [c.c_void_p] * 3
     lib.eb200_selftest_fe.argtypes = [c.c_int, c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.eb200_selftest_gtab.argtypes = [c.c_int, c.c_void_p, c.c_size_t]
     _lib = lib

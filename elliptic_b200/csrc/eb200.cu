@@ -9,6 +9,7 @@
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
 #include "ecdsa_sw_body.cuh"
+#include "ed25519_body.cuh"
 
 using namespace eb;
 
@@ -184,6 +185,29 @@ __global__ void sw_selftest_fe_kernel(int op, size_t n, const u32* a, const u32*
 }
 
 // ---------------------------------------------------------------------------
+// ed25519 / curve25519 kernels
+__global__ void __launch_bounds__(128) ed_gtab_kernel(u32* gtab) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)ED_GWINDOWS * ED_GENTRIES) return;
+  ed_gtab_entry((int)(t / ED_GENTRIES), (int)(t % ED_GENTRIES), gtab + t * 24);
+}
+__global__ void __launch_bounds__(128, 3)
+ed25519_verify_kernel(size_t N, const uint8_t* __restrict__ R, const uint8_t* __restrict__ S,
+                      const uint8_t* __restrict__ A, const uint8_t* __restrict__ h,
+                      const u32* __restrict__ gtab, u32* __restrict__ atab, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = ed25519_verify_item(i, R, S, A, h, gtab, atab);
+}
+__global__ void __launch_bounds__(128, 4)
+x25519_derive_kernel(size_t N, const uint8_t* __restrict__ priv, const uint8_t* __restrict__ pubx,
+                     uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = x25519_derive_item(i, priv, pubx, out);
+}
+
+// ---------------------------------------------------------------------------
 // context
 namespace {
 constexpr int MAX_CHUNKS = 16;
@@ -270,6 +294,15 @@ int ensure_table(int curve) {
   }
   if (curve == EB200_CURVE_P256) return sw_ensure_table<P256>(curve);
   if (curve == EB200_CURVE_P384) return sw_ensure_table<P384>(curve);
+  if (curve == EB200_CURVE_ED25519) {
+    if (g.gtab[curve]) return EB200_OK;
+    size_t entries = (size_t)ED_GWINDOWS * ED_GENTRIES;
+    CK(cudaMalloc(&g.gtab[curve], entries * 24 * 4));
+    ed_gtab_kernel<<<(unsigned)((entries + 127) / 128), 128, 0, g.stream>>>(g.gtab[curve]);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g.stream));
+    return EB200_OK;
+  }
   return EB200_ERR_UNSUPPORTED;
 }
 
@@ -444,7 +477,7 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   if (rc) return rc;
   const size_t len = curve_len(curve), pb = pub_item_bytes(len, pub_fmt);
   int chunks = 1;
-  if (n >= ((size_t)1 << 17)) chunks = 8;
+  if (n >= ((size_t)1 << 18)) chunks = 4;     // 2^18-item chunks keep the grid tail small (r01: 8 chunks cost 10%)
   if (n >= ((size_t)1 << 22)) chunks = MAX_CHUNKS;
   size_t per = (n + chunks - 1) / chunks;
   per = (per + 127) & ~(size_t)127;
@@ -498,6 +531,116 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   g.timing.d2h_ms = t;                                                       // exposed tail copy
   g.timing.kernel_ms = total;                                                // whole call on the GPU timeline
   g.timing.launches = launches;
+  return EB200_OK;
+}
+
+// ---- EdDSA (ed25519) verify ---------------------------------------------------------------
+size_t eb200_eddsa_verify_workspace_bytes(size_t n) { return align256((size_t)ED_ATAB_WORDS * 4 * n); }
+
+int eb200_eddsa_verify_batch_dev(size_t n, const uint8_t* d_R, const uint8_t* d_S, const uint8_t* d_A,
+                                 const uint8_t* d_h, uint8_t* d_status, void* d_workspace, void* stream) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (n && (!d_R || !d_S || !d_A || !d_h || !d_status || !d_workspace)) return EB200_ERR_ARG;
+  int rc = ensure_table(EB200_CURVE_ED25519);
+  if (rc) return rc;
+  if (n == 0) return EB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaEventRecord(g.ev[1], st));
+  CK(cudaEventRecord(g.ev[4], st));
+  ed25519_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, d_R, d_S, d_A, d_h, g.gtab[EB200_CURVE_ED25519],
+                                                                   (u32*)d_workspace, d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  CK(cudaEventRecord(g.ev[2], st));
+  g.timing.launches = 1;
+  g.dev_timing_pending = true;
+  return EB200_OK;
+}
+
+int eb200_eddsa_verify_batch(size_t n, const uint8_t* R, const uint8_t* S, const uint8_t* A, const uint8_t* h,
+                             uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (n == 0) return EB200_OK;
+  if (!R || !S || !A || !h || !status) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(EB200_CURVE_ED25519);
+  if (rc) return rc;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * 128))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, eb200_eddsa_verify_workspace_bytes(n)))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *dR = g.d_in, *dS = dR + 32 * n, *dA = dS + 32 * n, *dh = dA + 32 * n;
+  cudaStream_t st = g.stream;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(dR, R, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dS, S, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dA, A, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dh, h, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  ed25519_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dR, dS, dA, dh, g.gtab[EB200_CURVE_ED25519],
+                                                                   (u32*)g.d_ws, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  g.timing.main_kernel_ms = g.timing.kernel_ms;
+  g.timing.launches = 1;
+  return EB200_OK;
+}
+
+// ---- curve25519 ECDH derive -------------------------------------------------------------------
+int eb200_x25519_derive_batch_dev(size_t n, const uint8_t* d_priv, const uint8_t* d_pubx, uint8_t* d_out,
+                                  uint8_t* d_status, void* stream) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (n && (!d_priv || !d_pubx || !d_out || !d_status)) return EB200_ERR_ARG;
+  if (n == 0) return EB200_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaEventRecord(g.ev[1], st));
+  CK(cudaEventRecord(g.ev[4], st));
+  x25519_derive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, d_priv, d_pubx, d_out, d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  CK(cudaEventRecord(g.ev[2], st));
+  g.timing.launches = 1;
+  g.dev_timing_pending = true;
+  return EB200_OK;
+}
+
+int eb200_x25519_derive_batch(size_t n, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (n == 0) return EB200_OK;
+  if (!priv || !pubx || !out || !status) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * 96))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *dk = g.d_in, *dx = dk + 32 * n, *dout = dx + 32 * n;
+  cudaStream_t st = g.stream;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(dk, priv, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dx, pubx, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  x25519_derive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dk, dx, dout, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(out, dout, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  g.timing.main_kernel_ms = g.timing.kernel_ms;
+  g.timing.launches = 1;
   return EB200_OK;
 }
 

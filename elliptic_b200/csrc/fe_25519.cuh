@@ -1,0 +1,201 @@
+// fe_25519.cuh -- arithmetic in GF(2^255 - 19) for ed25519 / curve25519.
+//
+// Replaces bn.js `Red` over the P25519 pseudo-Mersenne prime (reference
+// dist/elliptic.js:7027-7051 P25519.imulK, 6904-6934 MPrime.ireduce, 7106-7175 Red ops,
+// 7177-7232 Red.sqrt (Tonelli-Shanks), 7234-7242 Red.invm) on the EdDSA-verify and
+// X25519-style ECDH paths.  8 x 32-bit limbs in registers, values weakly reduced to
+// [0, 2^256) (2^256 = 38 mod p); canonical residues only where the reference exposes them.
+#pragma once
+#include "limbs.cuh"
+#if defined(__CUDACC__)
+#ifndef EB_SQR8_INCLUDED
+#define EB_SQR8_INCLUDED
+namespace eb {
+#include "sqr8_gen.inc"
+}
+#endif
+#endif
+
+namespace eb {
+
+struct f25 { u32 v[8]; };
+
+EB_HD f25 f25_zero() { f25 r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+EB_HD f25 f25_one() { f25 r = f25_zero(); r.v[0] = 1; return r; }
+EB_HD f25 f25_small(u32 k) { f25 r = f25_zero(); r.v[0] = k; return r; }
+
+// fold a 512-bit value to [0, 2^256): lo + 38*hi, twice
+EB_HD void f25_reduce512(u32* r, const u32* t) {
+  u32 A[9];
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    c += (u64)t[8 + j] * 38u + t[j];
+    A[j] = (u32)c; c >>= 32;
+  }
+  A[8] = (u32)c;                       // < 38 + 1
+  c = (u64)A[8] * 38u + A[0];
+  r[0] = (u32)c; c >>= 32;
+#pragma unroll
+  for (int j = 1; j < 8; j++) {
+    c += A[j];
+    r[j] = (u32)c; c >>= 32;
+  }
+  // c in {0,1}: wrapped value < 38*39, adding 38 cannot carry out again
+  u32 k = (u32)c;
+  c = (u64)r[0] + (k ? 38u : 0u);
+  r[0] = (u32)c; c >>= 32;
+  r[1] += (u32)c;
+}
+
+EB_HD f25 f25_mul_inl(const f25& a, const f25& b) {
+  u32 t[16];
+  mul_wide<8>(t, a.v, b.v);
+  f25 r;
+  f25_reduce512(r.v, t);
+  return r;
+}
+EB_HD f25 f25_sqr_inl(const f25& a) {
+  u32 t[16];
+#if defined(__CUDA_ARCH__)
+  sqr_wide8_ptx(t, a.v);
+#else
+  mul_wide<8>(t, a.v, a.v);
+#endif
+  f25 r;
+  f25_reduce512(r.v, t);
+  return r;
+}
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__ f25 f25_mul(f25 a, f25 b) { return f25_mul_inl(a, b); }
+__host__ __device__ __noinline__ f25 f25_sqr(f25 a) { return f25_sqr_inl(a); }
+#else
+EB_HD f25 f25_mul(const f25& a, const f25& b) { return f25_mul_inl(a, b); }
+EB_HD f25 f25_sqr(const f25& a) { return f25_sqr_inl(a); }
+#endif
+
+EB_HD f25 f25_add(const f25& a, const f25& b) {
+  f25 r;
+  u32 cy = add_n<8>(r.v, a.v, b.v);
+  u32 t[8] = {cy ? 38u : 0u, 0, 0, 0, 0, 0, 0, 0};
+  cy = add_n<8>(r.v, r.v, t);
+  r.v[0] += cy ? 38u : 0u;             // second wrap: value is < 38 then
+  return r;
+}
+EB_HD f25 f25_sub(const f25& a, const f25& b) {
+  f25 r;
+  u32 bw = sub_n<8>(r.v, a.v, b.v);
+  u32 t[8] = {bw ? 38u : 0u, 0, 0, 0, 0, 0, 0, 0};
+  bw = sub_n<8>(r.v, r.v, t);
+  r.v[0] -= bw ? 38u : 0u;             // second borrow: value is >= 2^256 - 38, low limb >= 2^32 - 38
+  return r;
+}
+EB_HD f25 f25_neg(const f25& a) { return f25_sub(f25_zero(), a); }
+EB_HD f25 f25_dbl(const f25& a) { return f25_add(a, a); }
+
+// a * k, k < 2^26
+EB_HD f25 f25_mul_small(const f25& a, u32 k) {
+  f25 r;
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    c += (u64)a.v[j] * k;
+    r.v[j] = (u32)c; c >>= 32;
+  }
+  u64 m = c * 38u;                      // < 2^32
+  u32 t[8] = {(u32)m, (u32)(m >> 32), 0, 0, 0, 0, 0, 0};
+  u32 cy = add_n<8>(r.v, r.v, t);
+  r.v[0] += cy ? 38u : 0u;
+  return r;
+}
+
+// canonical residue in [0, p), p = 2^255 - 19
+EB_HD f25 f25_normalize(const f25& a) {
+  f25 r = a;
+  // fold bit 255: v = (v mod 2^255) + 19 * (v >> 255)   -> < 2^255 + 19
+  u32 top = r.v[7] >> 31;
+  r.v[7] &= 0x7FFFFFFFu;
+  u32 t[8] = {top ? 19u : 0u, 0, 0, 0, 0, 0, 0, 0};
+  add_n<8>(r.v, r.v, t);
+  // conditional subtract p (twice is never needed: value < 2^255 + 19 < 2p)
+  const u32 p[8] = {0xFFFFFFEDu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x7FFFFFFFu};
+  f25 d;
+  u32 bw = sub_n<8>(d.v, r.v, p);
+  cmov_n<8>(r.v, d.v, bw == 0);
+  return r;
+}
+EB_HD bool f25_is_zero(const f25& a) { f25 n = f25_normalize(a); return is_zero_n<8>(n.v); }
+EB_HD bool f25_eq(const f25& a, const f25& b) { return f25_is_zero(f25_sub(a, b)); }
+EB_HD bool f25_is_odd(const f25& a) { return f25_normalize(a).v[0] & 1; }
+EB_HD f25 f25_cmov(const f25& a, const f25& b, bool c) {
+  f25 r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c ? b.v[i] : a.v[i];
+  return r;
+}
+
+EB_HD f25 f25_sqr_n(f25 a, int n) { for (int i = 0; i < n; i++) a = f25_sqr(a); return a; }
+
+// a^(2^250 - 1) and a^11, the shared stem of the classic curve25519 addition chains
+EB_HD f25 f25_pow_2_250_1(const f25& a, f25* a11) {
+  f25 z2 = f25_sqr(a);
+  f25 z8 = f25_sqr_n(z2, 2);
+  f25 z9 = f25_mul(z8, a);
+  f25 z11 = f25_mul(z9, z2);
+  f25 z22 = f25_sqr(z11);
+  f25 z_5_0 = f25_mul(z22, z9);                         // 2^5 - 1
+  f25 z_10_0 = f25_mul(f25_sqr_n(z_5_0, 5), z_5_0);
+  f25 z_20_0 = f25_mul(f25_sqr_n(z_10_0, 10), z_10_0);
+  f25 z_40_0 = f25_mul(f25_sqr_n(z_20_0, 20), z_20_0);
+  f25 z_50_0 = f25_mul(f25_sqr_n(z_40_0, 10), z_10_0);
+  f25 z_100_0 = f25_mul(f25_sqr_n(z_50_0, 50), z_50_0);
+  f25 z_200_0 = f25_mul(f25_sqr_n(z_100_0, 100), z_100_0);
+  f25 z_250_0 = f25_mul(f25_sqr_n(z_200_0, 50), z_50_0);
+  *a11 = z11;
+  return z_250_0;
+}
+// a^(p-2) = a^(2^255 - 21): inverse; 0 -> 0 (bn.js _invmp(0) == 0, dist:6568-6579)
+EB_HD f25 f25_inv(const f25& a) {
+  f25 a11;
+  f25 t = f25_pow_2_250_1(a, &a11);
+  return f25_mul(f25_sqr_n(t, 5), a11);
+}
+// a^((p-5)/8) = a^(2^252 - 3)
+EB_HD f25 f25_pow_p58(const f25& a) {
+  f25 a11;
+  f25 t = f25_pow_2_250_1(a, &a11);
+  return f25_mul(f25_sqr_n(t, 2), a);
+}
+// a^((p-1)/2) = a^(2^254 - 10): Legendre symbol (0, 1 or p-1)
+EB_HD f25 f25_legendre(const f25& a) {
+  // 2^254 - 10 = (2^250 - 1) * 2^4 + 6
+  f25 a11;
+  f25 t = f25_pow_2_250_1(a, &a11);
+  f25 a2 = f25_sqr(a);
+  f25 a6 = f25_mul(f25_sqr(a2), a2);
+  return f25_mul(f25_sqr_n(t, 4), a6);
+}
+
+EB_HD f25 f25_sqrt_m1() {   // 2^((p-1)/4)
+  f25 r;
+  const u32 v[8] = {0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u};
+  for (int i = 0; i < 8; i++) r.v[i] = v[i];
+  return r;
+}
+EB_HD f25 f25_d() {         // ed25519 d (curves.js:157)
+  f25 r;
+  const u32 v[8] = {0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu};
+  for (int i = 0; i < 8; i++) r.v[i] = v[i];
+  return r;
+}
+EB_HD f25 f25_2d() {
+  f25 r;
+  const u32 v[8] = {0x26b2f159u, 0xebd69b94u, 0x8283b156u, 0x00e0149au, 0xeef3d130u, 0x198e80f2u, 0x56dffce7u, 0x2406d9dcu};
+  for (int i = 0; i < 8; i++) r.v[i] = v[i];
+  return r;
+}
+
+EB_HD f25 f25_load(const u32* src) { f25 a; for (int i = 0; i < 8; i++) a.v[i] = src[i]; return a; }
+EB_HD void f25_store(u32* dst, const f25& a) { for (int i = 0; i < 8; i++) dst[i] = a.v[i]; }
+
+}  // namespace eb

@@ -22,6 +22,8 @@ _CURVES = {
     "p256": dict(id=nat.CURVE_P256, len=32,
                  n=0xffffffff00000000ffffffffffffffffbce6faada7179e84f3b9cac2fc632551,
                  p=2**256 - 2**224 + 2**192 + 2**96 - 1),
+    "curve25519": dict(id=nat.CURVE_CURVE25519, len=32,
+                       n=0x1000000000000000000000000000000014def9dea2f79cd65812631a5cf5d3ed, p=2**255 - 19),
     "p384": dict(id=nat.CURVE_P384, len=48,
                  n=0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
                  p=2**384 - 2**128 - 2**96 + 2**32 - 1),
@@ -264,6 +266,37 @@ class EC:
             if st[i] in (nat.ST_TRUE, nat.ST_FALSE, nat.ST_NEEDS_HOST):
                 st[i] = v
         return st
+
+    # ---- ECDH --------------------------------------------------------------------------------------------
+    def derive_batch(self, privs, pubs):
+        """Batch of `ec.keyFromPrivate(priv).derive(ec.keyFromPublic(pub).getPublic())`
+        (ec/key.js:76-82, 102-107) on curve25519.  privs: ints / hex / bytes; pubs: the peer's x as
+        int / hex / big-endian bytes (mont.js:46-48).  Returns (list of int-or-None, statuses)."""
+        if self.name != "curve25519":
+            raise EllipticError("derive_batch: only curve25519 is accelerated")
+        lib = nat.init(self._device)
+        n = len(privs)
+        k = np.zeros((n, 32), np.uint8)
+        x = np.zeros((n, 32), np.uint8)
+        for i in range(n):
+            kv = _bn(privs[i]) % self.n                      # _importPrivate: umod n
+            xv = _bn(pubs[i])
+            if xv >> 256:
+                xv %= self._c["p"]
+            k[i] = np.frombuffer(kv.to_bytes(32, "big"), np.uint8)
+            x[i] = np.frombuffer(xv.to_bytes(32, "big"), np.uint8)
+        out = np.zeros((n, 32), np.uint8)
+        st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_x25519_derive_batch(n, k.ctypes.data, x.ctypes.data, out.ctypes.data, st.ctypes.data))
+        vals = [int.from_bytes(out[i].tobytes(), "big") if st[i] == nat.ST_TRUE else None for i in range(n)]
+        return vals, st
+
+    def derive(self, priv, pub):
+        """KeyPair.prototype.derive: the shared x as an int, or raises like the reference."""
+        vals, st = self.derive_batch([priv], [pub])
+        if st[0] == nat.ST_TRUE:
+            return vals[0]
+        raise EllipticError(_THROW_MSG.get(int(st[0]), "status %d" % int(st[0])))
 
     def verify(self, msg, signature, key, enc=None, options=None):
         """EC.prototype.verify (ec/index.js:188-229): bool, or raises."""

@@ -88,6 +88,31 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream);
 
+/* Batch of EDDSA.prototype.verify (lib/elliptic/eddsa/index.js:52-63) on ed25519.
+ *   R, S : the two 32-byte halves of each signature as on the wire (eddsa/signature.js:17-40)
+ *   A    : 32-byte encoded public keys (eddsa/key.js:17-30)
+ *   h    : SHA512(R || A || M) as a little-endian integer reduced mod n, 32 bytes LE (hashInt,
+ *          eddsa/index.js:65-70) -- computed by the caller (the host wrapper hashes with hashlib /
+ *          the N-API shim with hash.js); h MUST be < n.
+ * status: TRUE / FALSE, or THROW_INVALID_POINT / THROW_ASSERT where the reference throws while
+ * decoding R or A (edwards.js:84, bn.js Red.sqrt assertion). */
+int eb200_eddsa_verify_batch(size_t n, const uint8_t* R, const uint8_t* S, const uint8_t* A,
+                             const uint8_t* h, uint8_t* status);
+size_t eb200_eddsa_verify_workspace_bytes(size_t n);
+int eb200_eddsa_verify_batch_dev(size_t n, const uint8_t* d_R, const uint8_t* d_S, const uint8_t* d_A,
+                                 const uint8_t* d_h, uint8_t* d_status, void* d_workspace, void* stream);
+
+/* Batch of KeyPair.prototype.derive (lib/elliptic/ec/key.js:102-107) on curve25519:
+ *   priv : n x 32 bytes big-endian, the key pair's private scalar as the reference holds it
+ *          (reduced mod n at import, ec/key.js:76-82; no clamping)
+ *   pubx : n x 32 bytes big-endian x coordinate of the peer point (mont.js:46-48 decodePoint)
+ *   out  : n x 32 bytes big-endian shared x (BN -> toArray('be', 32)); zeroed when the call throws
+ * status: TRUE = value returned; THROW_ASSERT = the reference throws inside validate()
+ *         (twist point: Red.sqrt assertion, mont.js:21-28). */
+int eb200_x25519_derive_batch(size_t n, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status);
+int eb200_x25519_derive_batch_dev(size_t n, const uint8_t* d_priv, const uint8_t* d_pubx, uint8_t* d_out,
+                                  uint8_t* d_status, void* stream);
+
 /* Self-test hooks used by the parity tests (device arithmetic vs the oracle).
  * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_small(b[0]), 6 normalize, 7 inv, 8 sqrt candidate.
  * a, b, out: n x 8 little-endian 32-bit limbs (host pointers). */

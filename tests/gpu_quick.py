@@ -11,10 +11,12 @@ from elliptic_b200 import _native as nat
 from elliptic_b200.ec import EC
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+curve = sys.argv[2] if len(sys.argv) > 2 else "secp256k1"
+seed = {"secp256k1": 0xE1110002, "p256": 0xE1110256, "p384": 0xE1110384}[curve]
 t = time.time()
-ds = benchdata.gen_secp256k1_verify(n, cache_dir="/tmp/eb200_cache")
+ds = benchdata.gen_ecdsa_verify(curve, n, seed=seed, cache_dir="/tmp/eb200_cache")
 print("gen %.1fs" % (time.time() - t), flush=True)
-ec = EC("secp256k1")
+ec = EC(curve)
 res = []
 for it in range(4):
     t = time.time()

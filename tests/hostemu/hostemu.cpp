@@ -103,3 +103,52 @@ extern "C" void he_sw_verify(int curve, size_t N, const uint8_t* e, const uint8_
   if (curve == 2) sw_verify_host<P256>(N, e, r, s, pub, status);
   else sw_verify_host<P384>(N, e, r, s, pub, status);
 }
+
+// ---------------------------------------------------------------------------
+// ed25519 verify / curve25519 derive through the same bodies
+#include "../../elliptic_b200/csrc/ed25519_body.cuh"
+extern "C" void he_ed25519_verify(size_t N, const uint8_t* R, const uint8_t* S, const uint8_t* A, const uint8_t* h, uint8_t* status) {
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)ED_GWINDOWS * ED_GENTRIES * 24);
+    ed_ext base = ed_identity();
+    ed_G(&base.x, &base.y);
+    base.t = f25_mul(base.x, base.y);
+    for (int j = 0; j < ED_GWINDOWS; j++) {
+      ed_cached cb = ed_to_cached(base);
+      ed_ext acc = ed_identity();
+      for (int i = 0; i < ED_GENTRIES; i++) {
+        f25 zi = f25_inv(acc.z);
+        f25 x = f25_mul(acc.x, zi), y = f25_mul(acc.y, zi);
+        u32* o = &gtab[((size_t)j * ED_GENTRIES + i) * 24];
+        f25_store(o, f25_normalize(f25_add(y, x)));
+        f25_store(o + 8, f25_normalize(f25_sub(y, x)));
+        f25_store(o + 16, f25_normalize(f25_mul(f25_mul(x, y), f25_2d())));
+        acc = ed_add_cached(acc, cb);
+      }
+      for (int k = 0; k < ED_GW; k++) base = ed_dbl(base);
+    }
+  }
+  std::vector<u32> atab((size_t)ED_ATAB_WORDS * N);
+  for (size_t i = 0; i < N; i++) status[i] = ed25519_verify_item(i, R, S, A, h, gtab.data(), atab.data());
+}
+extern "C" void he_x25519_derive(size_t N, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = x25519_derive_item(i, priv, pubx, out);
+}
+extern "C" void he_f25_op(int op, const u32* a, const u32* b, u32* out) {
+  f25 A = f25_load(a), B = f25_load(b), R;
+  switch (op) {
+    case 0: R = f25_mul(A, B); break;
+    case 1: R = f25_sqr(A); break;
+    case 2: R = f25_add(A, B); break;
+    case 3: R = f25_sub(A, B); break;
+    case 4: R = f25_neg(A); break;
+    case 5: R = f25_mul_small(A, b[0]); break;
+    case 6: R = f25_normalize(A); break;
+    case 7: R = f25_inv(A); break;
+    case 8: R = f25_pow_p58(A); break;
+    case 9: R = f25_legendre(A); break;
+    default: R = f25_zero();
+  }
+  f25_store(out, R);
+}

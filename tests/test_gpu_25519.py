@@ -1,0 +1,58 @@
+"""GPU parity tests: ed25519 EdDSA verify and curve25519 ECDH derive vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ed25519_verify_parity(native):
+    from elliptic_b200.eddsa import EDDSA as GpuEd
+    from oracle.ref_py.eddsa import EDDSA
+    from ed_items import ed_items, ed_expected
+    ed, ged = EDDSA(), GpuEd()
+    items = ed_items()
+    arr = lambda k: np.frombuffer(b"".join(it[k] for it in items), np.uint8).reshape(-1, 32)
+    h = np.frombuffer(b"".join(ed.hash_int(it[0], it[2], it[3]).to_bytes(32, "little") for it in items), np.uint8).reshape(-1, 32)
+    st = ged.verify_batch_packed(arr(0), arr(1), arr(2), h)
+    exp = [ed_expected(ed, it) for it in items]
+    bad = [(i, int(st[i]), exp[i]) for i in range(len(items)) if int(st[i]) != exp[i]]
+    assert not bad, bad[:10]
+    assert {0, 1, 2, 5} <= set(exp)
+
+
+def test_ed25519_reference_argument_forms(native):
+    """test/ed25519-test.js:44-85 through the single-item API: hex strings and byte arrays."""
+    import gzip, json, os
+    from elliptic_b200.eddsa import EDDSA as GpuEd
+    from elliptic_b200.ec import EllipticError
+    data = json.load(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "ed25519_sign_input.json.gz"), "rt"))
+    ged = GpuEd()
+    for v in data["vectors"][:24]:
+        assert ged.verify(v["msg"], v["sig"], v["pk"]) is True
+        assert ged.verify(list(bytes.fromhex(v["msg"])), list(bytes.fromhex(v["sig"])), list(bytes.fromhex(v["pk"]))) is True
+        assert ged.verify(v["msg"] + "00", v["sig"], v["pk"]) is False
+    v = data["vectors"][5]
+    with pytest.raises(EllipticError, match="Signature has invalid size"):
+        ged.verify(v["msg"], v["sig"][:-2], v["pk"])
+    with pytest.raises(EllipticError, match="Assertion failed|invalid point"):
+        ged.verify(v["msg"], v["sig"], "02" + "00" * 31)
+
+
+def test_curve25519_derive_parity(native):
+    from elliptic_b200.ec import EC as GpuEC
+    from elliptic_b200 import _native as nat
+    from oracle.ref_py.ec import EC
+    from oracle.ref_py import curves
+    from ed_items import x_items, x_expected
+    ec, c = EC("curve25519"), curves.get("curve25519").curve
+    its = x_items(ec.n, count=300)
+    vals, st = GpuEC("curve25519").derive_batch([k for k, _ in its], [x for _, x in its])
+    for (k, x), v, s in zip(its, vals, st):
+        es, ev = x_expected(ec, c, k, x)
+        assert int(s) == es and (v or 0) == ev, (k, x)
+    # reference KAT (test/curve-test.js:348-356) and ECDH agreement (test/ecdh-test.js:8-29)
+    g = GpuEC("curve25519")
+    assert "%x" % g.derive(6, 9) == "26954ccdc99ebf34f8f1dde5e6bb080685fec73640494c28f9fe0bfa8c794531"
+    a, b = 0x1111111111111111111111, 0x2222222222222222222222222
+    pa, pb = g.derive(a, 9), g.derive(b, 9)
+    assert g.derive(a, pb) == g.derive(b, pa)

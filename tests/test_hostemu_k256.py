@@ -92,3 +92,26 @@ def test_sw_verify_pipeline_against_oracle(he, name, cid, ln):
     st = (ctypes.c_uint8 * n)()
     he.he_sw_verify(cid, ctypes.c_size_t(n), col(0), col(1), col(2), pub, st)
     assert [int(v) for v in st] == [sw_expected(ec, ln, it) for it in items]
+
+
+def test_ed25519_and_x25519_bodies_against_oracle(he):
+    from oracle.ref_py.eddsa import EDDSA
+    from oracle.ref_py.ec import EC
+    from oracle.ref_py import curves
+    from ed_items import ed_items, ed_expected, x_items, x_expected
+    ed = EDDSA()
+    items = ed_items(limit=20)
+    n = len(items)
+    cat = lambda k: b"".join(it[k] for it in items)
+    h = b"".join(ed.hash_int(it[0], it[2], it[3]).to_bytes(32, "little") for it in items)
+    st = (ctypes.c_uint8 * n)()
+    he.he_ed25519_verify(ctypes.c_size_t(n), cat(0), cat(1), cat(2), h, st)
+    assert [int(v) for v in st] == [ed_expected(ed, it) for it in items]
+    ec, c = EC("curve25519"), curves.get("curve25519").curve
+    its = x_items(ec.n, count=24)
+    m = len(its)
+    out, st = (ctypes.c_uint8 * (32 * m))(), (ctypes.c_uint8 * m)()
+    he.he_x25519_derive(ctypes.c_size_t(m), b"".join(k.to_bytes(32, "big") for k, _ in its),
+                        b"".join(x.to_bytes(32, "big") for _, x in its), out, st)
+    for i, (k, x) in enumerate(its):
+        assert (st[i], int.from_bytes(bytes(out[32 * i:32 * i + 32]), "big")) == x_expected(ec, c, k, x)
