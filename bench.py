@@ -177,6 +177,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = nat.init(local)
     ds = dataset(rank, world)

@@ -8,6 +8,7 @@
 #include <mutex>
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
+#include "ecdsa_k256_replay.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
 
@@ -46,6 +47,20 @@ k256_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __r
   if (i >= N) return;
   if (pre && pre[i]) { status[i] = pre[i]; return; }   // the reference throws while importing the key
   status[i] = verify_item(i, N, pub, r, ws, gtab, qtab);
+}
+
+// Exact replay of the reference's own GLV/JSF/wNAF schedule for the items the fast kernel flagged
+// (un-validated off-curve keys).  Divergent by nature; flagged items are rare.
+__global__ void __launch_bounds__(128) k256_replay_tab_kernel(u32* tab) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 2 * REPLAY_NAF_PTS) rp_tab_entry(t, tab + 16 * t);
+}
+__global__ void __launch_bounds__(128)
+k256_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s,
+                   const uint8_t* __restrict__ pub, const u32* __restrict__ tab, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
+  status[i] = rp_verify_item(i, e, r, s, pub, tab);
 }
 
 // SEC1 decode (BaseCurve.decodePoint, lib/elliptic/curve/base.js:270-292; pointFromX short.js:187-204)
@@ -216,6 +231,7 @@ struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   u32* gtab[8] = {};
+  u32* replay_tab = nullptr;          // secp256k1: the reference's wnd-7 NAF table of G and its beta image
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
   uint8_t* d_ws = nullptr; size_t d_ws_cap = 0;
   uint8_t* d_status = nullptr; size_t d_status_cap = 0;
@@ -289,6 +305,9 @@ int ensure_table(int curve) {
     CK(cudaMalloc(&g.gtab[curve], entries * 16 * 4));
     k256_gtab_kernel<<<(unsigned)((entries + 127) / 128), 128, 0, g.stream>>>(g.gtab[curve]);
     CK(cudaGetLastError());
+    CK(cudaMalloc(&g.replay_tab, (size_t)REPLAY_TAB_WORDS * 4));
+    k256_replay_tab_kernel<<<2, 128, 0, g.stream>>>(g.replay_tab);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(g.stream));
     return EB200_OK;
   }
@@ -336,6 +355,10 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     if (ev_main0) CK(cudaEventRecord(ev_main0, st));
     unsigned vb = (unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK);
     k256_verify_kernel<<<vb, EB_VERIFY_BLOCK, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+    CK(cudaGetLastError());
+    if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
+    k256_replay_kernel<<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.replay_tab, d_status);
+    cnt++;
   } else if (curve == EB200_CURVE_P256) {
     sw_prep_kernel<P256><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
     CK(cudaGetLastError());
@@ -393,6 +416,7 @@ int eb200_init(int device) {
     if (!g.ev_done[i]) CK(cudaEventCreate(&g.ev_done[i]));
   }
   for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   g.device = device;
   g.ready = true;
   // the headline curve's table is built eagerly; the others on first use
@@ -406,6 +430,7 @@ int eb200_shutdown(void) {
   if (!g.ready) return EB200_OK;
   cudaSetDevice(g.device);
   for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   cudaFree(g.d_in); g.d_in = nullptr; g.d_in_cap = 0;
   cudaFree(g.d_ws); g.d_ws = nullptr; g.d_ws_cap = 0;
   cudaFree(g.d_status); g.d_status = nullptr; g.d_status_cap = 0;

@@ -152,3 +152,22 @@ extern "C" void he_f25_op(int op, const u32* a, const u32* b, u32* out) {
   }
   f25_store(out, R);
 }
+
+// ---------------------------------------------------------------------------
+// exact replay of the reference schedule (off-curve keys)
+#include "../../elliptic_b200/csrc/ecdsa_k256_replay.cuh"
+static std::vector<u32>& replay_tab() {
+  static std::vector<u32> tab;
+  if (tab.empty()) {
+    tab.resize(REPLAY_TAB_WORDS);
+    for (int t = 0; t < 2 * REPLAY_NAF_PTS; t++) rp_tab_entry(t, &tab[16 * t]);
+  }
+  return tab;
+}
+extern "C" void he_replay_jmuladd(const u32* u1, const u32* u2, const u32* qx, const u32* qy, u32* xyz) {
+  ge_jac r = rp_jmul_add(u1, u2, load_fe(qx), load_fe(qy), replay_tab().data());
+  store_fe(xyz, fe_normalize(r.x)); store_fe(xyz + 8, fe_normalize(r.y)); store_fe(xyz + 16, fe_normalize(r.z));
+}
+extern "C" void he_replay_verify(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = rp_verify_item(i, e, r, s, pub, replay_tab().data());
+}

@@ -125,12 +125,14 @@ def _edge_items(ec, rnd):
     return items
 
 
-def _expected(ec, item):
+def _expected(ec, item, replay=False):
+    """replay=False: the fast kernel alone (off-curve keys are flagged 4); replay=True: the product
+    path, where flagged items are re-run through the exact-replay kernel and get the reference's answer."""
     e, r, s, x, y = item
     n = ec.n
     if not (1 <= r < n and 1 <= s < n):
         return 0
-    if not ec.curve.validate(ec.curve.point(x, y)):
+    if not replay and not ec.curve.validate(ec.curve.point(x, y)):
         return 4
     ev = e if e < n else e - n
     return int(ec.verify(ev.to_bytes(32, "big"), {"r": r, "s": s}, {"x": x, "y": y}))
@@ -145,10 +147,27 @@ def test_verify_parity_edge_cases(native):
     pack = lambda idx: np.frombuffer(b"".join(it[idx].to_bytes(32, "big") for it in items), np.uint8).reshape(-1, 32)
     pub = np.concatenate([pack(3), pack(4)], axis=1)
     st = GpuEC("secp256k1").verify_batch_packed(pack(0), pack(1), pack(2), pub)
-    exp = [_expected(ec, it) for it in items]
+    exp = [_expected(ec, it, replay=True) for it in items]
     bad = [(i, int(st[i]), exp[i]) for i in range(len(items)) if int(st[i]) != exp[i]]
     assert not bad, bad[:10]
-    assert 1 in exp and 0 in exp and 4 in exp
+    assert 1 in exp and 0 in exp
+
+
+def test_off_curve_keys_get_the_reference_answer(native):
+    """Un-validated off-curve keys (ec/key.js:95): the exact-replay kernel must agree with the C
+    restatement of the reference's schedule (itself checked against the Python oracle)."""
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle import c_oracle
+    rnd = random.Random(31)
+    n_items = 4096
+    rb = lambda k: np.frombuffer(rnd.randbytes(32 * k), np.uint8).reshape(k, 32).copy()
+    e, r, s = rb(n_items), rb(n_items), rb(n_items)
+    r[:, 0] &= 0x7F; s[:, 0] &= 0x7F                      # keep r, s < n
+    pub = np.concatenate([rb(n_items), rb(n_items)], axis=1)
+    pub[::7, :32] = 0                                    # x = 0
+    pub[3::11, 32:] = 0                                  # y = 0
+    st = GpuEC("secp256k1").verify_batch_packed(e, r, s, pub)
+    assert np.array_equal(st, c_oracle.verify_batch(e, r, s, pub, 4))
 
 
 def test_verify_reference_argument_forms(native):
@@ -170,8 +189,10 @@ def test_verify_reference_argument_forms(native):
     assert gec.verify(msg, der.hex(), hybrid.hex(), "hex") is True
     with pytest.raises(Exception):
         gec.verify(msg, der.hex(), (bytes([7 - (Q.y & 1)]) + Q.encode()[1:]).hex(), "hex")
+    off = {"x": Q.x, "y": Q.y + 1}                       # not on the curve: the reference still answers
+    assert gec.verify(msg, der.hex(), off) is ec.verify(msg, der.hex(), off, "hex")
     with pytest.raises(NeedsReferencePath):
-        gec.verify(msg, der.hex(), {"x": Q.x, "y": Q.y + 1})
+        GpuEC("p256").verify(msg, der.hex(), {"x": 5, "y": 7})
     # _truncateToN with a longer digest (64 bytes): reference shifts right
     long_msg = hashlib.sha512(b"hello").digest()
     sig2 = ec.sign(long_msg, d)
