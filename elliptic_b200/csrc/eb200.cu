@@ -49,6 +49,23 @@ k256_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __r
   status[i] = verify_item(i, N, pub, r, ws, gtab, qtab);
 }
 
+__global__ void __launch_bounds__(128) k256_prep_recover_kernel(size_t N, const uint8_t* __restrict__ e,
+                                                                const uint8_t* __restrict__ r,
+                                                                const uint8_t* __restrict__ s,
+                                                                u32* __restrict__ ws, u32* __restrict__ scratch) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  prep_thread(tid, T, N, e, r, s, ws, scratch, 1);
+}
+__global__ void __launch_bounds__(EB_VERIFY_BLOCK, EB_VERIFY_MINBLOCKS)
+k256_recover_kernel(size_t N, const uint8_t* __restrict__ r, const uint8_t* __restrict__ recid,
+                    const u32* __restrict__ ws, const u32* __restrict__ gtab, u32* __restrict__ qtab,
+                    uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = recover_item(i, N, r, recid, ws, gtab, qtab, out);
+}
+
 // Exact replay of the reference's own GLV/JSF/wNAF schedule for the items the fast kernel flagged
 // (un-validated off-curve keys).  Divergent by nature; flagged items are rare.
 __global__ void __launch_bounds__(128) k256_replay_tab_kernel(u32* tab) {
@@ -556,6 +573,52 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   g.timing.d2h_ms = t;                                                       // exposed tail copy
   g.timing.kernel_ms = total;                                                // whole call on the GPU timeline
   g.timing.launches = launches;
+  return EB200_OK;
+}
+
+// ---- ECDSA public-key recovery (secp256k1) ------------------------------------------------
+int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s,
+                              const uint8_t* recid, uint8_t* out_xy, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (n == 0) return EB200_OK;
+  if (!e || !r || !s || !recid || !out_xy || !status) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(curve);
+  if (rc) return rc;
+  WsLayout L = ws_layout(curve, n);
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (3 * 32 + 1 + 64) + 256))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, L.total))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *d_e = g.d_in, *d_r = d_e + 32 * n, *d_s = d_r + 32 * n, *d_out = d_s + 32 * n, *d_id = d_out + 64 * n;
+  cudaStream_t st = g.stream;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_r, r, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_s, s, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_id, recid, n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
+  k256_prep_recover_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_r, d_s, (u32*)(g.d_ws + L.ws), (u32*)(g.d_ws + L.scratch));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[4], st));
+  k256_recover_kernel<<<(unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK), EB_VERIFY_BLOCK, 0, st>>>(
+      n, d_r, d_id, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(out_xy, d_out, 64 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
+  g.timing.launches = 2;
   return EB200_OK;
 }
 

@@ -30,7 +30,7 @@ namespace eb {
 
 enum : uint8_t {
   ST_FALSE = 0, ST_TRUE = 1, ST_THROW_INVALID_POINT = 2, ST_THROW_NOT_VALIDATED = 3,
-  ST_NEEDS_HOST = 4, ST_THROW_ASSERT = 5, ST_THROW_POINT_FORMAT = 6,
+  ST_NEEDS_HOST = 4, ST_THROW_ASSERT = 5, ST_THROW_POINT_FORMAT = 6, ST_INFINITY = 7, ST_THROW_SECOND_KEY = 8,
 };
 
 // workspace layout (SoA, word-major so lanes are coalesced): PREP_WORDS words per item
@@ -116,8 +116,11 @@ EB_HD void gtab_entry(int j, int idx, u32* out16) {
 // prep: thread `tid` of `T` handles items tid, tid+T, ... (up to PREP_BATCH).
 // e, r, s: N x 32 bytes big-endian.  ws: PREP_WORDS x N words.
 // scratch: 8 x N words (prefix products).
+// mode 0 (verify, ec/index.js:199-207): invert s; u1 = e/s, u2 = r/s; r, s outside [1, n-1] -> FALSE.
+// mode 1 (recoverPubKey, ec/index.js:250-258): invert r; u1 = -e/r, u2 = s/r; no range checks
+//         (r = 0 mod n gives rInv = 0 exactly like BN.invm, i.e. the point at infinity).
 EB_HD void prep_thread(size_t tid, size_t T, size_t N, const uint8_t* e, const uint8_t* r,
-                       const uint8_t* s, u32* ws, u32* scratch) {
+                       const uint8_t* s, u32* ws, u32* scratch, int mode = 0) {
   u32 R2[8], one[8], nn[8];
   K256N::r2(R2); K256N::r1(one); K256N::n(nn);
   u32 prod[8];
@@ -132,9 +135,14 @@ EB_HD void prep_thread(size_t tid, size_t T, size_t N, const uint8_t* e, const u
     load_be<8>(sv, s + 32 * i);
     load_be<8>(rv, r + 32 * i);
     bool ok = sc_in_range(sv) && sc_in_range(rv);   // ec/index.js:199-202
-    if (!ok) invalid_mask |= 1u << j;
     u32 sm[8];
-    sc_mont_mul(sm, sv, R2);
+    if (mode == 1) {
+      sc_mont_mul(sm, rv, R2);                      // r mod n, Montgomery form
+      ok = !is_zero_n<8>(sm);
+    } else {
+      sc_mont_mul(sm, sv, R2);
+    }
+    if (!ok) invalid_mask |= 1u << j;
     cmov_n<8>(sm, one, !ok);
     // scratch[i] = prefix product BEFORE this item
     for (int w = 0; w < 8; w++) scratch[(size_t)w * N + i] = prod[w];
@@ -150,18 +158,26 @@ EB_HD void prep_thread(size_t tid, size_t T, size_t N, const uint8_t* e, const u
     bool ok = !((invalid_mask >> j) & 1);
     u32 sv[8], rv[8], ev[8], sm[8], pre[8], sinv[8], t[8];
     load_be<8>(sv, s + 32 * i);
-    sc_mont_mul(sm, sv, R2);
+    load_be<8>(rv, r + 32 * i);
+    sc_mont_mul(sm, mode == 1 ? rv : sv, R2);
     cmov_n<8>(sm, one, !ok);
     for (int w = 0; w < 8; w++) pre[w] = scratch[(size_t)w * N + i];
     sc_mont_mul(sinv, inv, pre);      // s_i^-1 (Montgomery form)
     sc_mont_mul(t, inv, sm);          // drop s_i from the running inverse
     copy_n<8>(inv, t);
-    u32 flags = ok ? 0 : FL_INVALID;
-    load_be<8>(rv, r + 32 * i);
+    u32 flags = (ok || mode == 1) ? 0 : FL_INVALID;
     load_be<8>(ev, e + 32 * i);
     u32 u1[8], u2[8];
-    sc_mont_mul(u1, ev, sinv);        // e * s^-1 mod n   (ec/index.js:206)
-    sc_mont_mul(u2, rv, sinv);        // r * s^-1 mod n   (ec/index.js:207)
+    if (mode == 1) {
+      u32 zero8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      cmov_n<8>(sinv, zero8, !ok);    // invm(0) = 0
+      sc_mont_mul(u1, ev, sinv);      // e / r
+      if (!is_zero_n<8>(u1)) sub_n<8>(u1, nn, u1);   // s1 = (n - e) * rInv mod n   (ec/index.js:251)
+      sc_mont_mul(u2, sv, sinv);      // s2 = s * rInv mod n         (ec/index.js:252)
+    } else {
+      sc_mont_mul(u1, ev, sinv);      // e * s^-1 mod n   (ec/index.js:206)
+      sc_mont_mul(u2, rv, sinv);      // r * s^-1 mod n   (ec/index.js:207)
+    }
     // u1 odd-ify: u1' = n - u1 when u1 is even (then the G part is negated)
     if ((u1[0] & 1) == 0) {
       sub_n<8>(u1, nn, u1);
@@ -190,15 +206,8 @@ EB_HD void prep_thread(size_t tid, size_t T, size_t N, const uint8_t* e, const u
 EB_HD void store_fe(u32* dst, const fe& a) { for (int i = 0; i < 8; i++) dst[i] = a.v[i]; }
 EB_HD fe load_fe(const u32* src) { fe a; for (int i = 0; i < 8; i++) a.v[i] = src[i]; return a; }
 
-EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t* r,
-                          const u32* ws, const u32* gtab, u32* qtab) {
-  u32 flags = ws[(size_t)18 * N + i];
-  if (flags & FL_INVALID) return ST_FALSE;
-  ge_aff Q;
-  Q.x = fe_from_be(pub + 64 * i);
-  Q.y = fe_from_be(pub + 64 * i + 32);
-  if (!aff_on_curve(Q)) return ST_NEEDS_HOST;
-
+// u1*G + u2*Q for an ON-CURVE Q, scalars as prepared by prep_thread in ws.  Jacobian result.
+EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32* ws, const u32* gtab, u32* qtab) {
   // ---- per-item table: (2k+1)*Q, k = 0..7, as affine points on an isomorphic
   // curve y^2 = x^3 + 7*Zg^6 (the a = 0 formulas never use b), Zg = zglobal.
   u32* tab = qtab + (size_t)i * QTAB_WORDS;
@@ -278,6 +287,18 @@ EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t*
     P.y = load_fe(ent + 8);
     acc = jac_madd(acc, aff_neg_if(P, neg));
   }
+  return acc;
+}
+
+EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t* r,
+                          const u32* ws, const u32* gtab, u32* qtab) {
+  u32 flags = ws[(size_t)18 * N + i];
+  if (flags & FL_INVALID) return ST_FALSE;
+  ge_aff Q;
+  Q.x = fe_from_be(pub + 64 * i);
+  Q.y = fe_from_be(pub + 64 * i + 32);
+  if (!aff_on_curve(Q)) return ST_NEEDS_HOST;
+  ge_jac acc = k256_dsm(i, N, Q, flags, ws, gtab, qtab);
 
   // ---- accept iff R != O and x(R) == r (mod n)   (ec/index.js:222-228, short.js:908-925)
   if (fe_is_zero(acc.z)) return ST_FALSE;
@@ -292,6 +313,37 @@ EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t*
     if (fe_eq(acc.x, fe_mul(rn, z2))) return ST_TRUE;
   }
   return ST_FALSE;
+}
+
+// EC.prototype.recoverPubKey (ec/index.js:231-259): Q = r^-1 (s*R - e*G), R = pointFromX(r or r+n, odd).
+// recid: 1 byte per item (0..3).  out: 64 bytes x||y big-endian.  Status: ST_TRUE = point returned,
+// ST_INFINITY = the reference returns the point at infinity, ST_THROW_INVALID_POINT (short.js:195),
+// ST_THROW_SECOND_KEY ('Unable to find sencond key candinate', ec/index.js:243-244).
+EB_HD uint8_t recover_item(size_t i, size_t N, const uint8_t* r, const uint8_t* recid,
+                           const u32* ws, const u32* gtab, u32* qtab, uint8_t* out) {
+  for (int b = 0; b < 64; b++) out[64 * i + b] = 0;
+  u32 j = recid[i];
+  bool odd = j & 1, second = (j >> 1) & 1;
+  u32 rv[8];
+  load_be<8>(rv, r + 32 * i);
+  const u32 pmn[8] = {0x2fc9baeeu, 0x402da172u, 0x50b75fc4u, 0x45512319u, 0x00000001u, 0, 0, 0};  // p mod n = p - n
+  if (second && geq_n<8>(rv, pmn)) return ST_THROW_SECOND_KEY;
+  fe x; copy_n<8>(x.v, rv);
+  if (second) { u32 nn[8]; K256N::n(nn); add_n<8>(x.v, rv, nn); }      // r + n < p here
+  fe seven = fe_zero(); seven.v[0] = 7;
+  fe y2 = fe_add(fe_mul(fe_sqr(x), x), seven);
+  fe y = fe_sqrt_candidate(y2);
+  if (!fe_eq(fe_sqr(y), y2)) return ST_THROW_INVALID_POINT;
+  if (fe_is_odd(y) != odd) y = fe_neg(y);
+  ge_aff R; R.x = x; R.y = y;
+  u32 flags = ws[(size_t)18 * N + i];
+  ge_jac acc = k256_dsm(i, N, R, flags, ws, gtab, qtab);
+  if (fe_is_zero(acc.z)) return ST_INFINITY;
+  ge_aff q = jac_to_aff(acc);
+  fe qx = fe_normalize(q.x), qy = fe_normalize(q.y);
+  store_be<8>(out + 64 * i, qx.v);
+  store_be<8>(out + 64 * i + 32, qy.v);
+  return ST_TRUE;
 }
 
 }  // namespace eb

@@ -45,6 +45,7 @@ _THROW_MSG = {
     nat.ST_THROW_NOT_VALIDATED: "public point not validated",
     nat.ST_THROW_ASSERT: "Assertion failed",
     nat.ST_THROW_POINT_FORMAT: "Unknown point format",
+    nat.ST_THROW_SECOND_KEY: "Unable to find sencond key candinate",
 }
 
 
@@ -266,6 +267,49 @@ class EC:
             if st[i] in (nat.ST_TRUE, nat.ST_FALSE, nat.ST_NEEDS_HOST):
                 st[i] = v
         return st
+
+    # ---- public-key recovery -----------------------------------------------------------------------------
+    def recover_pub_key_batch(self, msgs, sigs, js, enc=None):
+        """Batch of EC.prototype.recoverPubKey (ec/index.js:231-259).  msgs as `new BN(msg)` takes them
+        (int / hex / bytes, NOT truncated), sigs as Signature takes them, js the recovery params.
+        Returns (points, statuses): points[i] = (x, y), None for the point at infinity / a throw."""
+        if self.name != "secp256k1":
+            raise EllipticError("recover_pub_key_batch: only secp256k1 is accelerated")
+        lib = nat.init(self._device)
+        n = len(msgs)
+        e = np.zeros((n, 32), np.uint8); r = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+        rid = np.zeros(n, np.uint8)
+        for i in range(n):
+            if (3 & js[i]) != js[i]:
+                raise EllipticError("The recovery param is more than two bits")      # ec/index.js:232
+            rv, sv = self._signature_enc(sigs[i], enc)
+            ev = _bn(msgs[i]) if not isinstance(msgs[i], (bytes, bytearray, list, tuple)) else int.from_bytes(_to_array(msgs[i]), "big")
+            e[i] = np.frombuffer((ev % self.n).to_bytes(32, "big"), np.uint8)
+            r[i] = np.frombuffer((rv % (1 << 256)).to_bytes(32, "big"), np.uint8)
+            s[i] = np.frombuffer((sv % self.n).to_bytes(32, "big"), np.uint8)
+            rid[i] = js[i]
+        out = np.zeros((n, 64), np.uint8)
+        st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_ecdsa_recover_batch(self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data,
+                                                rid.ctypes.data, out.ctypes.data, st.ctypes.data))
+        pts = [(int.from_bytes(out[i, :32].tobytes(), "big"), int.from_bytes(out[i, 32:].tobytes(), "big"))
+               if st[i] == nat.ST_TRUE else None for i in range(n)]
+        return pts, st
+
+    def recover_pub_key(self, msg, signature, j, enc=None):
+        pts, st = self.recover_pub_key_batch([msg], [signature], [j], enc)
+        if st[0] in (nat.ST_TRUE, nat.ST_INFINITY):
+            return pts[0]
+        raise EllipticError(_THROW_MSG.get(int(st[0]), "status %d" % int(st[0])))
+
+    def _signature_enc(self, sig, enc):
+        """new Signature(sig, enc) as recoverPubKey calls it (enc passed through, ec/index.js:233)."""
+        if isinstance(sig, dict) or (hasattr(sig, "r") and hasattr(sig, "s")):
+            return self._signature(sig)
+        rs = parse_der(_to_array(sig, enc))
+        if rs is None:
+            raise EllipticError("Signature without r or s")
+        return rs
 
     # ---- ECDH --------------------------------------------------------------------------------------------
     def derive_batch(self, privs, pubs):

@@ -40,6 +40,8 @@ extern "C" {
                                            own single-item path for this item */
 #define EB200_ST_THROW_ASSERT 5         /* threw Error('Assertion failed') (bn.js sqrt / hybrid parity) */
 #define EB200_ST_THROW_POINT_FORMAT 6   /* threw Error('Unknown point format')  base.js:291 */
+#define EB200_ST_INFINITY 7             /* (recover) returned the point at infinity */
+#define EB200_ST_THROW_SECOND_KEY 8     /* (recover) threw Error('Unable to find sencond key candinate')  ec/index.js:244 */
 
 /* curve ids (names of lib/elliptic/curves.js presets) */
 #define EB200_CURVE_SECP256K1 1
@@ -87,6 +89,15 @@ size_t eb200_ecdsa_verify_workspace_bytes(int curve, size_t n);
 int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r,
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream);
+
+/* Batch of EC.prototype.recoverPubKey (lib/elliptic/ec/index.js:231-259), secp256k1:
+ *   e     : n x 32  `new BN(msg)` reduced mod n (NOT truncated -- the reference does not truncate here)
+ *   r, s  : n x 32  signature halves (no range check in the reference: r = 0 yields the point at infinity)
+ *   recid : n bytes, the recovery parameter j in 0..3 (bit 0 = y parity, bit 1 = use r + n)
+ *   out_xy: n x 64  recovered public key x || y big-endian (zeroed unless status is TRUE)
+ * status: TRUE (point written), INFINITY, THROW_INVALID_POINT (pointFromX, short.js:195), THROW_SECOND_KEY. */
+int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s,
+                              const uint8_t* recid, uint8_t* out_xy, uint8_t* status);
 
 /* Batch of EDDSA.prototype.verify (lib/elliptic/eddsa/index.js:52-63) on ed25519.
  *   R, S : the two 32-byte halves of each signature as on the wire (eddsa/signature.js:17-40)

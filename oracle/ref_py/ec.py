@@ -194,7 +194,8 @@ class EC:
             rp = self.curve.point_from_x(r + n, is_y_odd)
         else:
             rp = self.curve.point_from_x(r, is_y_odd)
-        r_inv = pow(signature.r, -1, n)
+        # BN.invm -> egcd (dist:6436-6516, 6624-6626): for r = 0 (mod n) the returned cofactor is 0
+        r_inv = pow(signature.r % n, -1, n) if signature.r % n else 0
         s1 = ((n - e) * r_inv) % n
         s2 = (s * r_inv) % n
         return self.g.mul_add(s1, rp, s2)

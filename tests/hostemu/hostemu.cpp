@@ -171,3 +171,11 @@ extern "C" void he_replay_jmuladd(const u32* u1, const u32* u2, const u32* qx, c
 extern "C" void he_replay_verify(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
   for (size_t i = 0; i < N; i++) status[i] = rp_verify_item(i, e, r, s, pub, replay_tab().data());
 }
+
+extern "C" void he_recover(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* recid,
+                           const u32* gtab, uint8_t* out, uint8_t* status) {
+  std::vector<u32> ws((size_t)PREP_WORDS * N), scratch((size_t)8 * N), qtab((size_t)QTAB_WORDS * N);
+  size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
+  for (size_t t = 0; t < T; t++) prep_thread(t, T, N, e, r, s, ws.data(), scratch.data(), 1);
+  for (size_t i = 0; i < N; i++) status[i] = recover_item(i, N, r, recid, ws.data(), gtab, qtab.data(), out);
+}

@@ -216,3 +216,22 @@ def test_verify_large_batch_properties(native):
         it = tuple(int.from_bytes(ds[k][i].tobytes(), "big") for k in ("e", "r", "s")) + (
             int.from_bytes(ds["pub"][i, :32].tobytes(), "big"), int.from_bytes(ds["pub"][i, 32:].tobytes(), "big"))
         assert int(st[i]) == _expected(ec, it), i
+
+
+def test_recover_pub_key_parity(native):
+    """EC.recoverPubKey (ec/index.js:231-259; test/ecdsa-test.js:467-490): every recovery param, the
+    second-key throw, x without a square root, r = 0 / r = n (point at infinity)."""
+    from elliptic_b200.ec import EC as GpuEC, EllipticError
+    from oracle.ref_py.ec import EC
+    from rec_items import rec_items, rec_expected
+    ec = EC("secp256k1")
+    items, truth = rec_items(ec, count=200)
+    gec = GpuEC("secp256k1")
+    pts, st = gec.recover_pub_key_batch([it[0] for it in items], [{"r": it[1] or "00", "s": it[2] or "00"} for it in items],
+                                        [it[3] for it in items])
+    for i, it in enumerate(items):
+        assert (int(st[i]), pts[i]) == rec_expected(ec, it), (i, it[3])
+        if i in truth:
+            assert pts[i] == truth[i]
+    with pytest.raises(EllipticError, match="sencond key"):
+        gec.recover_pub_key(5, {"r": ec.n - 1, "s": 3}, 2)

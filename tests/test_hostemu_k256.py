@@ -115,3 +115,25 @@ def test_ed25519_and_x25519_bodies_against_oracle(he):
                         b"".join(x.to_bytes(32, "big") for _, x in its), out, st)
     for i, (k, x) in enumerate(its):
         assert (st[i], int.from_bytes(bytes(out[32 * i:32 * i + 32]), "big")) == x_expected(ec, c, k, x)
+
+
+def test_recover_pub_key_body_against_oracle(he):
+    from oracle.ref_py.ec import EC
+    from rec_items import rec_items, rec_expected
+    ec = EC("secp256k1")
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    he.he_gtab_dims(ctypes.byref(W), ctypes.byref(E), ctypes.byref(B))
+    gtab = np.zeros(W.value * E.value * 16, np.uint32)
+    he.he_gtab_fast(gtab.ctypes.data_as(ctypes.c_void_p))
+    items, truth = rec_items(ec, count=12)
+    n = len(items)
+    e = b"".join((it[0] % ec.n).to_bytes(32, "big") for it in items)
+    r = b"".join((it[1] % 2**256).to_bytes(32, "big") for it in items)
+    s = b"".join((it[2] % ec.n).to_bytes(32, "big") for it in items)
+    out, st = (ctypes.c_uint8 * (64 * n))(), (ctypes.c_uint8 * n)()
+    he.he_recover(ctypes.c_size_t(n), e, r, s, bytes(it[3] for it in items), gtab.ctypes.data_as(ctypes.c_void_p), out, st)
+    for i, it in enumerate(items):
+        pt = (int.from_bytes(bytes(out[64 * i:64 * i + 32]), "big"), int.from_bytes(bytes(out[64 * i + 32:64 * i + 64]), "big"))
+        assert (st[i], pt if st[i] == 1 else None) == rec_expected(ec, it), i
+        if i in truth:
+            assert st[i] == 1 and pt == truth[i]
