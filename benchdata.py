@@ -167,12 +167,12 @@ if __name__ == "__main__":
 N_ED = 0x1000000000000000000000000000000014DEF9DEA2F79CD65812631A5CF5D3ED
 
 
-def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, cache_dir=None):
+def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, cache_dir=None, with_msgs=False):
     """Signatures are produced with libsodium (PyNaCl) -- a generator, not the code under test.
     1/64 items are forged the way test/ed25519-test.js:75-77 does (last message byte + 1)."""
     import nacl.signing
     if cache_dir:
-        path = os.path.join(cache_dir, "ed25519_%x_%d_%d_%d.npz" % (seed, n_items, n_keys, corrupt_every))
+        path = os.path.join(cache_dir, "ed25519m_%x_%d_%d_%d.npz" % (seed, n_items, n_keys, corrupt_every))
         if os.path.exists(path):
             z = np.load(path)
             return {k: z[k] for k in z.files}
@@ -183,6 +183,7 @@ def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, 
     S = np.zeros((n_items, 32), np.uint8)
     A = np.zeros((n_items, 32), np.uint8)
     H = np.zeros((n_items, 32), np.uint8)
+    M = np.zeros((n_items, 32), np.uint8)
     expected = np.ones(n_items, np.uint8)
     for i in range(n_items):
         j = i % n_keys
@@ -196,7 +197,8 @@ def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, 
         S[i] = np.frombuffer(sig[32:], np.uint8)
         A[i] = np.frombuffer(pubs[j], np.uint8)
         H[i] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
-    out = dict(R=R, S=S, A=A, h=H, expected=expected)
+        M[i] = np.frombuffer(msg, np.uint8)
+    out = dict(R=R, S=S, A=A, h=H, msgs=M, expected=expected)
     if cache_dir:
         os.makedirs(cache_dir, exist_ok=True)
         np.savez(path, **out)

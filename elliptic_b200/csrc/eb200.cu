@@ -9,6 +9,7 @@
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
 #include "ecdsa_k256_replay.cuh"
+#include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
 
@@ -64,6 +65,15 @@ k256_recover_kernel(size_t N, const uint8_t* __restrict__ r, const uint8_t* __re
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   status[i] = recover_item(i, N, r, recid, ws, gtab, qtab, out);
+}
+
+__global__ void __launch_bounds__(128)
+k256_sign_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
+                 const u32* __restrict__ gtab, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
+                 uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = k256_sign_item(i, e, priv, canonical, gtab, r, s, recid);
 }
 
 // Exact replay of the reference's own GLV/JSF/wNAF schedule for the items the fast kernel flagged
@@ -230,6 +240,13 @@ ed25519_verify_kernel(size_t N, const uint8_t* __restrict__ R, const uint8_t* __
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   status[i] = ed25519_verify_item(i, R, S, A, h, gtab, atab);
+}
+__global__ void __launch_bounds__(128)
+ed25519_hash_kernel(size_t N, const uint8_t* __restrict__ R, const uint8_t* __restrict__ A,
+                    const uint8_t* __restrict__ msgs, const u64* __restrict__ msg_off, uint8_t* __restrict__ h) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  ed25519_hash_item(i, R, A, msgs, msg_off, h);
 }
 __global__ void __launch_bounds__(128, 4)
 x25519_derive_kernel(size_t N, const uint8_t* __restrict__ priv, const uint8_t* __restrict__ pubx,
@@ -622,6 +639,45 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
   return EB200_OK;
 }
 
+// ---- ECDSA sign (secp256k1, RFC 6979 nonces on the GPU) -------------------------------------------------
+int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,
+                           uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (n == 0) return EB200_OK;
+  if (!e || !priv || !out_r || !out_s || !out_recid || !status) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(curve);
+  if (rc) return rc;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (4 * 32 + 1) + 256))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *d_e = g.d_in, *d_k = d_e + 32 * n, *d_r = d_k + 32 * n, *d_s = d_r + 32 * n, *d_id = d_s + 32 * n;
+  cudaStream_t st = g.stream;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_k, priv, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  k256_sign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, d_e, d_k, flags & EB200_SIGN_CANONICAL, g.gtab[curve],
+                                                              d_r, d_s, d_id, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(out_r, d_r, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_s, d_s, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_recid, d_id, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  g.timing.main_kernel_ms = g.timing.kernel_ms;
+  g.timing.launches = 1;
+  return EB200_OK;
+}
+
 // ---- EdDSA (ed25519) verify ---------------------------------------------------------------
 size_t eb200_eddsa_verify_workspace_bytes(size_t n) { return align256((size_t)ED_ATAB_WORDS * 4 * n); }
 
@@ -679,6 +735,54 @@ int eb200_eddsa_verify_batch(size_t n, const uint8_t* R, const uint8_t* S, const
   cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
   g.timing.main_kernel_ms = g.timing.kernel_ms;
   g.timing.launches = 1;
+  return EB200_OK;
+}
+
+// EdDSA verify from raw messages: SHA-512 on the GPU, then the same verify kernel.
+int eb200_eddsa_verify_batch_msgs(size_t n, const uint8_t* R, const uint8_t* S, const uint8_t* A,
+                                  const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (n == 0) return EB200_OK;
+  if (!R || !S || !A || !msg_off || !status || (!msgs && msg_off[n])) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(EB200_CURVE_ED25519);
+  if (rc) return rc;
+  size_t mbytes = (size_t)msg_off[n];
+  size_t off_bytes = (n + 1) * sizeof(uint64_t);
+  size_t base = align256(n * 128);
+  if ((rc = grow(&g.d_in, &g.d_in_cap, base + align256(off_bytes) + align256(mbytes + 1)))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, eb200_eddsa_verify_workspace_bytes(n)))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *dR = g.d_in, *dS = dR + 32 * n, *dA = dS + 32 * n, *dh = dA + 32 * n;
+  uint64_t* doff = (uint64_t*)(g.d_in + base);
+  uint8_t* dm = g.d_in + base + align256(off_bytes);
+  cudaStream_t st = g.stream;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(dR, R, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dS, S, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dA, A, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(doff, msg_off, off_bytes, cudaMemcpyHostToDevice, st));
+  if (mbytes) CK(cudaMemcpyAsync(dm, msgs, mbytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  ed25519_hash_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dR, dA, dm, doff, dh);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[4], st));
+  ed25519_verify_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dR, dS, dA, dh, g.gtab[EB200_CURVE_ED25519],
+                                                                   (u32*)g.d_ws, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
+  g.timing.launches = 2;
   return EB200_OK;
 }
 

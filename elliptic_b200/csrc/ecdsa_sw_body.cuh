@@ -9,10 +9,9 @@
 // over a fixed affine table; CIOS Montgomery field; exceptional cases in cold paths.
 #pragma once
 #include "fp_mont.cuh"
+#include "sw_params.cuh"
 
 namespace eb {
-
-#include "sw_params_gen.inc"
 
 template <class C>
 struct SW {

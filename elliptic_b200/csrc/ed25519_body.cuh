@@ -13,6 +13,8 @@
 // one exponentiation per decompression instead of inversion + Tonelli-Shanks.
 #pragma once
 #include "fe_25519.cuh"
+#include "sw_params.cuh"
+#include "sha2.cuh"
 
 namespace eb {
 
@@ -244,6 +246,28 @@ EB_HD uint8_t ed25519_verify_item(size_t i, const uint8_t* Rb, const uint8_t* Sb
   // S*G - h*A == R as affine points  (edwards.js:409-413)
   bool ok = f25_eq(acc.x, f25_mul(rx, acc.z)) && f25_eq(acc.y, f25_mul(ry, acc.z));
   return ok ? 1 : 0;
+}
+
+// EDDSA.hashInt for verify (eddsa/index.js:59,65-70): h = SHA512(Rencoded || pubBytes || message) as a
+// little-endian integer, mod n.  Writes 32 bytes little-endian.
+EB_HD void ed25519_hash_item(size_t i, const uint8_t* Rb, const uint8_t* Ab, const uint8_t* msgs,
+                             const u64* msg_off, uint8_t* h_out) {
+  sha512_ctx c;
+  sha512_init(&c);
+  sha512_update(&c, Rb + 32 * i, 32);
+  sha512_update(&c, Ab + 32 * i, 32);
+  sha512_update(&c, msgs + msg_off[i], (size_t)(msg_off[i + 1] - msg_off[i]));
+  uint8_t dg[64];
+  sha512_final(&c, dg);
+  typedef Fp<ED25519_FN> S;
+  S::fe lo, hi;
+  load_le<8>(lo.v, dg);
+  load_le<8>(hi.v, dg + 32);
+  S::fe r = S::add(S::from_mont(S::to_mont(lo)), S::to_mont(hi));   // lo mod n + hi * 2^256 mod n
+  for (int k = 0; k < 8; k++) {
+    h_out[32 * i + 4 * k] = (uint8_t)r.v[k]; h_out[32 * i + 4 * k + 1] = (uint8_t)(r.v[k] >> 8);
+    h_out[32 * i + 4 * k + 2] = (uint8_t)(r.v[k] >> 16); h_out[32 * i + 4 * k + 3] = (uint8_t)(r.v[k] >> 24);
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -268,6 +268,33 @@ class EC:
                 st[i] = v
         return st
 
+    # ---- signing ---------------------------------------------------------------------------------------------
+    def sign_batch(self, msgs, privs, canonical=False, msg_bit_length=None):
+        """Batch of EC.prototype.sign (ec/index.js:110-186) with the default hash and RFC 6979 nonces
+        (no `pers`, no custom `k`).  Returns (r list, s list, recoveryParam array)."""
+        if self.name != "secp256k1":
+            raise EllipticError("sign_batch: only secp256k1 is accelerated")
+        lib = nat.init(self._device)
+        n = len(msgs)
+        e = np.zeros((n, 32), np.uint8); d = np.zeros((n, 32), np.uint8)
+        for i in range(n):
+            ev = self._truncate_to_n(msgs[i], msg_bit_length)
+            if ev >> 256:
+                raise EllipticError("Can not sign message")                    # ec/index.js:136-137
+            e[i] = np.frombuffer(ev.to_bytes(32, "big"), np.uint8)
+            d[i] = np.frombuffer((_bn(privs[i]) % self.n).to_bytes(32, "big"), np.uint8)   # _importPrivate
+        r = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+        rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_ecdsa_sign_batch(self._c["id"], n, e.ctypes.data, d.ctypes.data, 1 if canonical else 0,
+                                             r.ctypes.data, s.ctypes.data, rec.ctypes.data, st.ctypes.data))
+        assert bool((st == nat.ST_TRUE).all())
+        return ([int.from_bytes(r[i].tobytes(), "big") for i in range(n)],
+                [int.from_bytes(s[i].tobytes(), "big") for i in range(n)], rec)
+
+    def sign(self, msg, priv, canonical=False):
+        r, s, rec = self.sign_batch([msg], [priv], canonical)
+        return {"r": r[0], "s": s[0], "recoveryParam": int(rec[0])}
+
     # ---- public-key recovery -----------------------------------------------------------------------------
     def recover_pub_key_batch(self, msgs, sigs, js, enc=None):
         """Batch of EC.prototype.recoverPubKey (ec/index.js:231-259).  msgs as `new BN(msg)` takes them

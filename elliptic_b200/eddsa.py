@@ -47,13 +47,45 @@ class EDDSA:
                                                status.ctypes.data))
         return status
 
-    def verify_batch(self, messages, sigs, pubs):
-        """EDDSA#verifyBatch: lists of the reference's own argument forms (hex strings / byte arrays)."""
+    def verify_batch_msgs_packed(self, R, S, A, msgs, msg_off):
+        """Like verify_batch_packed but takes the raw messages (concatenated bytes + n+1 offsets);
+        SHA-512 and the reduction mod n run on the GPU."""
+        lib = nat.init(self._device)
+        R, S, A = (np.ascontiguousarray(a, dtype=np.uint8) for a in (R, S, A))
+        msgs = np.ascontiguousarray(msgs, dtype=np.uint8)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = R.shape[0]
+        assert msg_off.shape == (n + 1,) and int(msg_off[n]) == msgs.size
+        status = np.empty(n, np.uint8)
+        nat.check(lib.eb200_eddsa_verify_batch_msgs(n, R.ctypes.data, S.ctypes.data, A.ctypes.data,
+                                                    msgs.ctypes.data if msgs.size else None, msg_off.ctypes.data,
+                                                    status.ctypes.data))
+        return status
+
+    def verify_batch(self, messages, sigs, pubs, gpu_hash=True):
+        """EDDSA#verifyBatch: lists of the reference's own argument forms (hex strings / byte arrays).
+        gpu_hash=False computes hashInt with hashlib on the host instead of on the GPU."""
         n = len(messages)
         R = np.zeros((n, 32), np.uint8)
         S = np.zeros((n, 32), np.uint8)
         A = np.zeros((n, 32), np.uint8)
         h = np.zeros((n, 32), np.uint8)
+        if gpu_hash:
+            ms = []
+            for i in range(n):
+                sig = _parse_bytes(sigs[i])
+                if len(sig) != 2 * self.encoding_length:
+                    raise EllipticError("Signature has invalid size")   # eddsa/signature.js:23-24
+                pub = _parse_bytes(pubs[i])
+                if len(pub) != self.encoding_length:
+                    raise EllipticError("unsupported public key length %d" % len(pub))
+                R[i] = np.frombuffer(sig[:32], np.uint8)
+                S[i] = np.frombuffer(sig[32:], np.uint8)
+                A[i] = np.frombuffer(pub, np.uint8)
+                ms.append(_parse_bytes(messages[i]))
+            off = np.zeros(n + 1, np.uint64)
+            off[1:] = np.cumsum([len(m) for m in ms])
+            return self.verify_batch_msgs_packed(R, S, A, np.frombuffer(b"".join(ms), np.uint8), off)
         for i in range(n):
             msg = _parse_bytes(messages[i])
             sig = _parse_bytes(sigs[i])

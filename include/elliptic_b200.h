@@ -90,6 +90,17 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream);
 
+/* Batch of EC.prototype.sign (lib/elliptic/ec/index.js:110-186), secp256k1, default hash (sha256) and no
+ * `pers` / custom `k`: RFC 6979 nonces from HMAC-DRBG(SHA-256) are generated on the GPU.
+ *   e    : n x 32  _truncateToN(msg) (ec/index.js:127), big-endian
+ *   priv : n x 32  private scalars as the key pair holds them (reduced mod n at import, ec/key.js:76-82)
+ *   flags: EB200_SIGN_CANONICAL = the `canonical` option (s <= n/2, recovery bit flipped)
+ *   out_r, out_s : n x 32 big-endian; out_recid : n bytes (recoveryParam)
+ * status: TRUE for every item (the reference's retry loop runs inside the kernel). */
+#define EB200_SIGN_CANONICAL 1u
+int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,
+                           uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status);
+
 /* Batch of EC.prototype.recoverPubKey (lib/elliptic/ec/index.js:231-259), secp256k1:
  *   e     : n x 32  `new BN(msg)` reduced mod n (NOT truncated -- the reference does not truncate here)
  *   r, s  : n x 32  signature halves (no range check in the reference: r = 0 yields the point at infinity)
@@ -109,6 +120,10 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
  * decoding R or A (edwards.js:84, bn.js Red.sqrt assertion). */
 int eb200_eddsa_verify_batch(size_t n, const uint8_t* R, const uint8_t* S, const uint8_t* A,
                              const uint8_t* h, uint8_t* status);
+/* Same, hashing on the GPU: msgs = all messages concatenated, message i = msgs[msg_off[i] .. msg_off[i+1])
+ * (msg_off has n+1 entries).  h = SHA512(R || A || M) mod n is computed in a first kernel. */
+int eb200_eddsa_verify_batch_msgs(size_t n, const uint8_t* R, const uint8_t* S, const uint8_t* A,
+                                  const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status);
 size_t eb200_eddsa_verify_workspace_bytes(size_t n);
 int eb200_eddsa_verify_batch_dev(size_t n, const uint8_t* d_R, const uint8_t* d_S, const uint8_t* d_A,
                                  const uint8_t* d_h, uint8_t* d_status, void* d_workspace, void* stream);

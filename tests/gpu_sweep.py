@@ -14,7 +14,7 @@ from elliptic_b200.ec import EC
 from elliptic_b200.eddsa import EDDSA
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "curve25519"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "ed25519_msgs", "curve25519", "k256_sign", "k256_recover"]
 CACHE = "/tmp/eb200_cache"
 res = {}
 for name in which:
@@ -28,6 +28,31 @@ for name in which:
         ds = benchdata.gen_ed25519_verify(n, cache_dir=CACHE)
         ed = EDDSA()
         run = lambda: ed.verify_batch_packed(ds["R"], ds["S"], ds["A"], ds["h"])
+    elif name == "ed25519_msgs":      # raw 32-byte messages, SHA-512 on the GPU
+        ds = benchdata.gen_ed25519_verify(n, cache_dir=CACHE, with_msgs=True)
+        ed = EDDSA()
+        off = np.arange(n + 1, dtype=np.uint64) * 32
+        run = lambda: ed.verify_batch_msgs_packed(ds["R"], ds["S"], ds["A"], ds["msgs"].reshape(-1), off)
+    elif name in ("k256_sign", "k256_recover"):
+        ds0 = benchdata.gen_ecdsa_verify("secp256k1", n, seed=0xE1110002, cache_dir=CACHE)
+        lib = nat.init(0)
+        rng = np.random.default_rng(7)
+        priv = rng.integers(0, 256, size=(n, 32), dtype=np.uint8); priv[:, 0] &= 0x7F; priv[:, 31] |= 1
+        r_o = np.zeros((n, 32), np.uint8); s_o = np.zeros((n, 32), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
+        ds = {"expected": np.ones(n, np.uint8)}
+        if name == "k256_sign":
+            def run():
+                nat.check(lib.eb200_ecdsa_sign_batch(1, n, ds0["e"].ctypes.data, priv.ctypes.data, 0, r_o.ctypes.data,
+                                                     s_o.ctypes.data, rec.ctypes.data, st.ctypes.data))
+                return st
+        else:
+            out = np.zeros((n, 64), np.uint8)
+            rid = (rng.integers(0, 2, size=n)).astype(np.uint8)
+            # valid signatures recover to *some* key for recid 0/1 unless x(R) has no sqrt for that parity: always has
+            def run():
+                nat.check(lib.eb200_ecdsa_recover_batch(1, n, ds0["e"].ctypes.data, ds0["r"].ctypes.data, ds0["s"].ctypes.data,
+                                                        rid.ctypes.data, out.ctypes.data, st.ctypes.data))
+                return np.where((st == 1) | (st == 2), 1, st).astype(np.uint8)
     else:
         ds = benchdata.gen_x25519_derive(n, cache_dir=CACHE)
         lib = nat.init(0)

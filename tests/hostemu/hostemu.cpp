@@ -179,3 +179,20 @@ extern "C" void he_recover(size_t N, const uint8_t* e, const uint8_t* r, const u
   for (size_t t = 0; t < T; t++) prep_thread(t, T, N, e, r, s, ws.data(), scratch.data(), 1);
   for (size_t i = 0; i < N; i++) status[i] = recover_item(i, N, r, recid, ws.data(), gtab, qtab.data(), out);
 }
+
+// ---------------------------------------------------------------------------
+#include "../../elliptic_b200/csrc/sha2.cuh"
+extern "C" void he_sha512(const uint8_t* p, size_t n, uint8_t* out) { sha512_ctx c; sha512_init(&c); sha512_update(&c, p, n); sha512_final(&c, out); }
+extern "C" void he_sha256(const uint8_t* p, size_t n, uint8_t* out) { sha256_ctx c; sha256_init(&c); sha256_update(&c, p, n); sha256_final(&c, out); }
+extern "C" void he_hmac256(const uint8_t* k, const uint8_t* a, size_t na, const uint8_t* b, size_t nb, uint8_t* out) { hmac_sha256(k, a, na, b, nb, 0, 0, out); }
+extern "C" void he_ed25519_hash(size_t N, const uint8_t* R, const uint8_t* A, const uint8_t* msgs, const u64* off, uint8_t* h) {
+  for (size_t i = 0; i < N; i++) ed25519_hash_item(i, R, A, msgs, off, h);
+}
+
+// ---------------------------------------------------------------------------
+#include "../../elliptic_b200/csrc/ecdsa_k256_sign.cuh"
+extern "C" void he_fe_inv_chain(const u32* a, u32* out) { store_fe(out, fe_inv_chain(load_fe(a))); }
+extern "C" void he_sign(size_t N, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,
+                        uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = k256_sign_item(i, e, priv, canonical, gtab, r, s, recid);
+}

@@ -56,3 +56,20 @@ def test_curve25519_derive_parity(native):
     a, b = 0x1111111111111111111111, 0x2222222222222222222222222
     pa, pb = g.derive(a, 9), g.derive(b, 9)
     assert g.derive(a, pb) == g.derive(b, pa)
+
+
+def test_ed25519_gpu_hashing_equals_host_hashing(native):
+    """hashInt on the GPU (SHA-512 + reduction mod n) vs hashlib, over the reference's sign.input messages
+    (lengths 0..1023 bytes) -- statuses must be identical and match the oracle."""
+    from elliptic_b200.eddsa import EDDSA as GpuEd
+    from oracle.ref_py.eddsa import EDDSA
+    from ed_items import ed_items, ed_expected
+    ed, ged = EDDSA(), GpuEd()
+    items = ed_items()
+    msgs = [it[3] for it in items]
+    sigs = [it[0] + it[1] for it in items]
+    pubs = [it[2] for it in items]
+    a = ged.verify_batch(msgs, sigs, pubs, gpu_hash=True)
+    b = ged.verify_batch(msgs, sigs, pubs, gpu_hash=False)
+    assert np.array_equal(a, b)
+    assert [int(v) for v in a] == [ed_expected(ed, it) for it in items]

@@ -235,3 +235,27 @@ def test_recover_pub_key_parity(native):
             assert pts[i] == truth[i]
     with pytest.raises(EllipticError, match="sencond key"):
         gec.recover_pub_key(5, {"r": ec.n - 1, "s": 3}, 2)
+
+
+def test_sign_batch_matches_reference_rfc6979(native):
+    """EC.sign (ec/index.js:110-186): r, s and recoveryParam must equal the oracle's (deterministic
+    RFC 6979 nonces from HMAC-DRBG/SHA-256 generated on the GPU), with and without `canonical`;
+    every signature must verify and recover to the signer's key."""
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    ec, gec = EC("secp256k1"), GpuEC("secp256k1")
+    rnd = random.Random(77)
+    msgs = [rnd.randbytes(32) for _ in range(96)] + [b"\x00" * 32, b"\xff" * 32, rnd.randbytes(48)]
+    privs = [rnd.randrange(1, ec.n) for _ in msgs]
+    privs[1], privs[2] = 1, ec.n - 1
+    for canonical in (False, True):
+        r, s, rec = gec.sign_batch(msgs, privs, canonical=canonical)
+        for i, (m, d) in enumerate(zip(msgs, privs)):
+            sig = ec.sign(m, d, canonical=canonical)
+            assert (r[i], s[i], int(rec[i])) == (sig.r, sig.s, sig.recovery_param), (i, canonical)
+    pubs = [ec.g.mul(d) for d in privs]
+    st = gec.verify_batch(msgs, [{"r": a, "s": b} for a, b in zip(r, s)], [{"x": q.x, "y": q.y} for q in pubs])
+    assert bool((st == 1).all())
+    pts, st2 = gec.recover_pub_key_batch([int.from_bytes(m, "big") >> max(0, 8 * len(m) - 256) for m in msgs],
+                                         [{"r": a, "s": b} for a, b in zip(r, s)], [int(v) for v in rec])
+    assert [p for p in pts] == [(q.x, q.y) for q in pubs]

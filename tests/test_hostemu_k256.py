@@ -137,3 +137,44 @@ def test_recover_pub_key_body_against_oracle(he):
         assert (st[i], pt if st[i] == 1 else None) == rec_expected(ec, it), i
         if i in truth:
             assert st[i] == 1 and pt == truth[i]
+
+
+def test_sign_and_hash_bodies_against_oracle(he):
+    """RFC 6979 signing body (HMAC-DRBG/SHA-256, fixed-base k*G, inversion chain) and EdDSA hashInt body."""
+    import hashlib
+    from oracle.ref_py.ec import EC
+    from oracle.ref_py.eddsa import EDDSA
+    from ed_items import ed_items
+    ec = EC("secp256k1")
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    he.he_gtab_dims(ctypes.byref(W), ctypes.byref(E), ctypes.byref(B))
+    gtab = np.zeros(W.value * E.value * 16, np.uint32)
+    he.he_gtab_fast(gtab.ctypes.data_as(ctypes.c_void_p))
+    rnd = random.Random(5)
+    items = [(rnd.randrange(ec.n), rnd.randrange(1, ec.n)) for _ in range(10)] + [(0, 1), (ec.n - 1, ec.n - 1)]
+    n = len(items)
+    e = b"".join(x.to_bytes(32, "big") for x, _ in items)
+    d = b"".join(y.to_bytes(32, "big") for _, y in items)
+    for canon in (0, 1):
+        r, s = (ctypes.c_uint8 * (32 * n))(), (ctypes.c_uint8 * (32 * n))()
+        rec, st = (ctypes.c_uint8 * n)(), (ctypes.c_uint8 * n)()
+        he.he_sign(ctypes.c_size_t(n), e, d, canon, gtab.ctypes.data_as(ctypes.c_void_p), r, s, rec, st)
+        for i, (ev, dv) in enumerate(items):
+            sig = ec.sign(ev.to_bytes(32, "big"), dv, canonical=bool(canon))
+            assert (int.from_bytes(bytes(r[32 * i:32 * i + 32]), "big"), int.from_bytes(bytes(s[32 * i:32 * i + 32]), "big"),
+                    rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1)
+    ed = EDDSA()
+    eit = ed_items(limit=16)
+    m = len(eit)
+    off = np.zeros(m + 1, np.uint64)
+    off[1:] = np.cumsum([len(it[3]) for it in eit])
+    h = (ctypes.c_uint8 * (32 * m))()
+    he.he_ed25519_hash(ctypes.c_size_t(m), b"".join(it[0] for it in eit), b"".join(it[2] for it in eit),
+                       b"".join(it[3] for it in eit), off.ctypes.data_as(ctypes.c_void_p), h)
+    assert bytes(h) == b"".join(ed.hash_int(it[0], it[2], it[3]).to_bytes(32, "little") for it in eit)
+    for nbytes in (0, 1, 55, 56, 63, 64, 111, 112, 127, 128, 129, 1000):
+        msg = rnd.randbytes(nbytes)
+        o = (ctypes.c_uint8 * 64)(); he.he_sha512(msg, ctypes.c_size_t(nbytes), o)
+        assert bytes(o) == hashlib.sha512(msg).digest()
+        o = (ctypes.c_uint8 * 32)(); he.he_sha256(msg, ctypes.c_size_t(nbytes), o)
+        assert bytes(o) == hashlib.sha256(msg).digest()
