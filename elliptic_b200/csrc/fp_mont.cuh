@@ -25,8 +25,121 @@ struct Fp {
   static EB_HD fe zero() { fe r; for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
   static EB_HD fe one() { fe r; P::r1(r.v); return r; }   // Montgomery form of 1
 
+#if defined(__CUDA_ARCH__)
+  // CIOS with two accumulators so that every (lo,hi) product pair stays on a fixed register pair
+  // (ptxas then emits one IMAD.WIDE.U32.X per 32x32+64 MAC and no realignment moves):
+  //   T = E + O * 2^32,  E takes the even-indexed limbs' products, O the odd-indexed ones.
+  // After a row, E[0] == 0; dividing by 2^32 swaps the roles: the old O becomes the new E (absorbing
+  // E[1], whose carry is exactly what the new O's lowest limb must receive), and the old E shifted
+  // down by two limbs becomes the new O -- the shift is done for free by the 3-address mad.
+  // Arrays carry two extra limbs because p256 / p384 / the group orders use every bit of their top limb.
+  // One PTX instruction per asm statement: with n0inv == 1 the multiplier m IS E[0], and a tied "+r"
+  // operand inside a multi-instruction asm would be overwritten before its second use.
+  template <bool FIRST>
+  static EB_D void cios_row(u32* E, u32* X, const u32* a, u32 bi, const u32* p) {
+    // X: previous even array on entry; rewritten in place as the new odd array.
+    if (!FIRST) asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(E[0]) : "r"(X[1]));
+#pragma unroll
+    for (int j = 1; j < N; j += 2) {
+      if (FIRST) {
+        if (j == 1) asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(X[0]) : "r"(a[1]), "r"(bi));
+        else asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(X[j - 1]) : "r"(a[j]), "r"(bi));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(X[j]) : "r"(a[j]), "r"(bi));
+      } else {
+        asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(X[j - 1]) : "r"(a[j]), "r"(bi), "r"(X[j + 1]));
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(X[j]) : "r"(a[j]), "r"(bi), "r"(X[j + 2]));
+      }
+    }
+    if (FIRST) { X[N] = 0; X[N + 1] = 0; }
+    else {
+      asm volatile("addc.cc.u32 %0, 0, 0;" : "=r"(X[N]));
+      asm volatile("addc.u32 %0, 0, 0;" : "=r"(X[N + 1]));
+    }
+    // E += even-indexed limbs of a times bi
+    if (FIRST) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(E[j]) : "r"(a[j]), "r"(bi));
+        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(E[j + 1]) : "r"(a[j]), "r"(bi));
+      }
+      E[N] = 0; E[N + 1] = 0;
+    } else {
+      asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[0]) : "r"(a[0]), "r"(bi));
+      asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[1]) : "r"(a[0]), "r"(bi));
+#pragma unroll
+      for (int j = 2; j < N; j += 2) {
+        asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[j]) : "r"(a[j]), "r"(bi));
+        asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[j + 1]) : "r"(a[j]), "r"(bi));
+      }
+      asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(E[N]));
+      asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N + 1]));
+    }
+    u32 m = E[0] * P::n0inv;
+    // O (= X) += odd-indexed limbs of p times m
+    asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(X[0]) : "r"(p[1]), "r"(m));
+    asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(X[1]) : "r"(p[1]), "r"(m));
+#pragma unroll
+    for (int j = 3; j < N; j += 2) {
+      asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(X[j - 1]) : "r"(p[j]), "r"(m));
+      asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(X[j]) : "r"(p[j]), "r"(m));
+    }
+    asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(X[N]));
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(X[N + 1]));
+    // E += even-indexed limbs of p times m   (E[0] becomes 0)
+    asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[0]) : "r"(p[0]), "r"(m));
+    asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[1]) : "r"(p[0]), "r"(m));
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(E[j]) : "r"(p[j]), "r"(m));
+      asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(E[j + 1]) : "r"(p[j]), "r"(m));
+    }
+    asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(E[N]));
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(E[N + 1]));
+  }
+  static EB_D fe mul_ptx(const fe& a, const fe& b) {
+    static_assert(N % 2 == 0, "PTX CIOS path is written for an even limb count");
+    u32 p[N]; P::mod(p);
+    u32 A[N + 3], B[N + 3];
+    A[N + 2] = 0; B[N + 2] = 0;
+    // row 0: E = A, new odd = B.  Afterwards roles alternate: the new even array is the old odd one.
+    cios_row<true>(A, B, a.v, b.v[0], p);
+#pragma unroll
+    for (int i = 1; i < N; i += 2) {
+      cios_row<false>(B, A, a.v, b.v[i], p);                 // even = B (old odd), A: old even -> new odd
+      if (i + 1 < N) cios_row<false>(A, B, a.v, b.v[i + 1], p);
+    }
+    // N even: the last row had even = B, odd = A.  T / 2^32 = (B >> 32) + A
+    u32 t[N + 1];
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(t[0]) : "r"(B[1]), "r"(A[0]));
+#pragma unroll
+    for (int k = 1; k < N; k++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(t[k]) : "r"(B[k + 1]), "r"(A[k]));
+    asm volatile("addc.u32 %0, %1, %2;" : "=r"(t[N]) : "r"(B[N + 1]), "r"(A[N]));
+    fe r, d;
+    u32 bw = sub_n<N>(d.v, t, p);
+    bool ge = t[N] != 0 || bw == 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = ge ? d.v[i] : t[i];
+    return r;
+  }
+#endif
+
   // a*b*R^-1 mod p.  Requires a < R, b < p (or a < p, b < R); result in [0, p).
+  // Out-of-line on the device (operands in registers): one copy of the ~250-instruction multiplier
+  // per field instead of one per use keeps the double/add loop inside the instruction cache.
+#if defined(__CUDACC__)
+  static __device__ __noinline__ fe mul_ol(fe a, fe b) { return mul_ptx_or_c(a, b); }
+#endif
   static EB_HD fe mul(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
+    return mul_ol(a, b);
+#else
+    return mul_ptx_or_c(a, b);
+#endif
+  }
+  static EB_HD fe mul_ptx_or_c(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_PORTABLE)
+    if (N % 2 == 0) return mul_ptx(a, b);
+#endif
     u32 p[N]; P::mod(p);
     u32 t[N + 2];
 #pragma unroll
