@@ -241,6 +241,24 @@ ed25519_verify_kernel(size_t N, const uint8_t* __restrict__ R, const uint8_t* __
   if (i >= N) return;
   status[i] = ed25519_verify_item(i, R, S, A, h, gtab, atab);
 }
+__global__ void f25_selftest_kernel(int op, size_t n, const u32* a, const u32* b, u32* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  f25 A = f25_load(a + 8 * i), B = f25_load(b + 8 * i), R;
+  switch (op) {
+    case 0: R = f25_mul(A, B); break;
+    case 1: R = f25_sqr(A); break;
+    case 2: R = f25_add(A, B); break;
+    case 3: R = f25_sub(A, B); break;
+    case 4: R = f25_neg(A); break;
+    case 5: R = f25_mul_small(A, b[8 * i]); break;
+    case 6: R = f25_normalize(A); break;
+    case 7: R = f25_inv(A); break;
+    case 8: R = f25_pow_p58(A); break;
+    default: R = f25_zero();
+  }
+  f25_store(out + 8 * i, R);
+}
 __global__ void __launch_bounds__(128)
 ed25519_hash_kernel(size_t N, const uint8_t* __restrict__ R, const uint8_t* __restrict__ A,
                     const uint8_t* __restrict__ msgs, const u64* __restrict__ msg_off, uint8_t* __restrict__ h) {
@@ -293,6 +311,9 @@ int grow(uint8_t** p, size_t* cap, size_t need) {
 }
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+size_t fe_len(int curve) {   // field-element bytes for the selftest hooks (also the 25519 curves)
+  return (curve == EB200_CURVE_P384) ? 48 : (curve >= EB200_CURVE_SECP256K1 && curve <= EB200_CURVE_CURVE25519) ? 32 : 0;
+}
 size_t curve_len(int curve) {
   switch (curve) {
     case EB200_CURVE_SECP256K1: case EB200_CURVE_P256: return 32;
@@ -838,11 +859,11 @@ int eb200_x25519_derive_batch(size_t n, const uint8_t* priv, const uint8_t* pubx
 
 int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
+  if (!fe_len(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
-  size_t bytes = n * curve_len(curve);
+  size_t bytes = n * fe_len(curve);
   u32 *da, *db, *dout;
   CK(cudaMalloc(&da, bytes)); CK(cudaMalloc(&db, bytes)); CK(cudaMalloc(&dout, bytes));
   CK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
@@ -850,6 +871,7 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
   unsigned nb = (unsigned)((n + 127) / 128);
   if (curve == EB200_CURVE_SECP256K1) k256_selftest_fe_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_P256) sw_selftest_fe_kernel<P256><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
+  else if (curve == EB200_CURVE_ED25519 || curve == EB200_CURVE_CURVE25519) f25_selftest_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else sw_selftest_fe_kernel<P384><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));

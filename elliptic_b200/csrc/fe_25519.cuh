@@ -24,8 +24,48 @@ EB_HD f25 f25_zero() { f25 r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; 
 EB_HD f25 f25_one() { f25 r = f25_zero(); r.v[0] = 1; return r; }
 EB_HD f25 f25_small(u32 k) { f25 r = f25_zero(); r.v[0] = k; return r; }
 
+#if defined(__CUDA_ARCH__)
+// Device fold as two 3-address carry chains + one merge (see fe_k256.cuh::fe_reduce512_ptx).
+EB_D void f25_reduce512_ptx(u32* r, const u32* t) {
+  const u32 K = 38u, Z = 0;
+  u32 E[9], O[9], A[9];
+#define F25_MADLO_CC(d, a, b, c) asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c))
+#define F25_MADCLO_CC(d, a, b, c) asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c))
+#define F25_MADCHI_CC(d, a, b, c) asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c))
+#define F25_ADD_CC(d, a, b) asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
+#define F25_ADDC_CC(d, a, b) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
+#define F25_ADDC(d, a, b) asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b))
+  F25_MADLO_CC(E[0], t[8], K, t[0]);   F25_MADCHI_CC(E[1], t[8], K, t[1]);
+  F25_MADCLO_CC(E[2], t[10], K, t[2]); F25_MADCHI_CC(E[3], t[10], K, t[3]);
+  F25_MADCLO_CC(E[4], t[12], K, t[4]); F25_MADCHI_CC(E[5], t[12], K, t[5]);
+  F25_MADCLO_CC(E[6], t[14], K, t[6]); F25_MADCHI_CC(E[7], t[14], K, t[7]);
+  F25_ADDC(E[8], Z, Z);
+  F25_MADLO_CC(O[1], t[9], K, Z);   F25_MADCHI_CC(O[2], t[9], K, Z);
+  F25_MADCLO_CC(O[3], t[11], K, Z); F25_MADCHI_CC(O[4], t[11], K, Z);
+  F25_MADCLO_CC(O[5], t[13], K, Z); F25_MADCHI_CC(O[6], t[13], K, Z);
+  F25_MADCLO_CC(O[7], t[15], K, Z); F25_MADCHI_CC(O[8], t[15], K, Z);
+  A[0] = E[0];
+  F25_ADD_CC(A[1], E[1], O[1]);
+#pragma unroll
+  for (int k = 2; k < 8; k++) F25_ADDC_CC(A[k], E[k], O[k]);
+  F25_ADDC(A[8], E[8], O[8]);                      // A < 39 * 2^256: A[8] <= 38
+  u32 c1;
+  F25_MADLO_CC(r[0], A[8], K, A[0]);               // A[8]*38 < 2^11: no high part
+#pragma unroll
+  for (int k = 1; k < 8; k++) F25_ADDC_CC(r[k], A[k], Z);
+  F25_ADDC(c1, Z, Z);
+  u32 kK = c1 * K;                                  // wrapped value < 2^11: adding 38 stays in limb 0..1
+  F25_ADD_CC(r[0], r[0], kK);
+  F25_ADDC(r[1], r[1], Z);
+}
+#endif
+
 // fold a 512-bit value to [0, 2^256): lo + 38*hi, twice
 EB_HD void f25_reduce512(u32* r, const u32* t) {
+#if defined(__CUDA_ARCH__) && !defined(EB_REDUCE_C)
+  f25_reduce512_ptx(r, t);
+  return;
+#endif
   u32 A[9];
   u64 c = 0;
 #pragma unroll

@@ -73,3 +73,42 @@ def test_ed25519_gpu_hashing_equals_host_hashing(native):
     b = ged.verify_batch(msgs, sigs, pubs, gpu_hash=False)
     assert np.array_equal(a, b)
     assert [int(v) for v in a] == [ed_expected(ed, it) for it in items]
+
+
+def test_f25519_field_bit_exact(native):
+    """PTX field ops mod 2^255 - 19 (weak representatives allowed, value mod p exact), edge values included."""
+    import random
+    from elliptic_b200 import _native as nat
+    P = 2**255 - 19
+    rnd = random.Random(21)
+    edge = [0, 1, 2, P - 1, P, P + 1, 2**256 - 1, 2**256 - 2, 2**255, 2**255 - 1, 19, 38, 2**256 - 38, 2**256 - 19,
+            2**256 - 2**32, (1 << 256) - 39, 2 * P, 2 * P + 37]
+    a = edge + [rnd.randrange(2**256) for _ in range(3000)]
+    b = [a[(7 * i + 3) % len(a)] for i in range(len(a))]
+    a += [x for x in edge for _ in edge]
+    b += [y for _ in edge for y in edge]
+
+    def limbs(vals):
+        m = np.zeros((len(vals), 8), np.uint32)
+        for i, v in enumerate(vals):
+            for k in range(8):
+                m[i, k] = (v >> (32 * k)) & 0xFFFFFFFF
+        return m
+
+    def run(op, x, y):
+        X, Y = limbs(x), limbs(y)
+        out = np.zeros_like(X)
+        nat.check(native.eb200_selftest_fe(nat.CURVE_ED25519, op, len(x), X.ctypes.data, Y.ctypes.data, out.ctypes.data))
+        return [sum(int(out[i, k]) << (32 * k) for k in range(8)) for i in range(len(x))]
+    for op, fn in ((0, lambda x, y: x * y), (1, lambda x, y: x * x), (2, lambda x, y: x + y), (3, lambda x, y: x - y), (4, lambda x, y: -x)):
+        for x, y, g in zip(a, b, run(op, a, b)):
+            assert g < 2**256 and g % P == fn(x, y) % P, (op, hex(x), hex(y))
+    ks = [121666 if i % 2 else 486662 for i in range(len(a))]
+    for x, k, g in zip(a, ks, run(5, a, ks)):
+        assert g % P == x * k % P
+    for x, g in zip(a, run(6, a, b)):
+        assert g == x % P
+    for x, g in zip(a[:48], run(7, a[:48], b[:48])):
+        assert g % P == pow(x % P, P - 2, P)
+    for x, g in zip(a[:48], run(8, a[:48], b[:48])):
+        assert g % P == pow(x % P, (P - 5) // 8, P)
