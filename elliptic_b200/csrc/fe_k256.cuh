@@ -165,7 +165,65 @@ EB_HD fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
 EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// Device add / sub: the 2^256 wrap touches only limbs 0..1 unless a carry leaves limb 1 (probability
+// 2^-32 on random data) -- that propagation, and the second wrap behind it, live in a cold branch.
+EB_D fe fe_add_ptx(const fe& a, const fe& b) {
+  fe r;
+  const u32 Z = 0;
+  u32 cy, c2;
+  EB_ADD_CC(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) EB_ADDC_CC(r.v[i], a.v[i], b.v[i]);
+  EB_ADDC(cy, Z, Z);
+  u32 kK = cy * K256_C0;
+  EB_ADD_CC(r.v[0], r.v[0], kK);
+  EB_ADDC_CC(r.v[1], r.v[1], cy);
+  EB_ADDC(c2, Z, Z);
+  if (c2) {
+    u32 c3;
+    EB_ADD_CC(r.v[2], r.v[2], c2);
+#pragma unroll
+    for (int i = 3; i < 8; i++) EB_ADDC_CC(r.v[i], r.v[i], Z);
+    EB_ADDC(c3, Z, Z);
+    u32 k3 = c3 * K256_C0;                 // wrapped twice: the value is now tiny, no further carry
+    EB_ADD_CC(r.v[0], r.v[0], k3);
+    EB_ADDC(r.v[1], r.v[1], c3);
+  }
+  return r;
+}
+EB_D fe fe_sub_ptx(const fe& a, const fe& b) {
+  fe r;
+  const u32 Z = 0;
+  u32 bw, b2;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int i = 1; i < 8; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+  asm volatile("subc.u32 %0, %1, %1;" : "=r"(bw) : "r"(Z));      // 0 or 0xFFFFFFFF
+  bw &= 1;
+  u32 kK = bw * K256_C0;
+  asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(kK));
+  asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(r.v[1]) : "r"(bw));
+  asm volatile("subc.u32 %0, %1, %1;" : "=r"(b2) : "r"(Z));
+  if (b2) {
+    u32 b3;
+    asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[2]) : "r"(1u));
+#pragma unroll
+    for (int i = 3; i < 8; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(r.v[i]) : "r"(Z));
+    asm volatile("subc.u32 %0, %1, %1;" : "=r"(b3) : "r"(Z));
+    b3 &= 1;
+    u32 k3 = b3 * K256_C0;                 // wrapped below zero twice: value is now >= 2^256 - 2c
+    asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(k3));
+    asm volatile("subc.u32 %0, %0, %1;" : "+r"(r.v[1]) : "r"(b3));
+  }
+  return r;
+}
+#endif
+
 EB_HD fe fe_add(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(EB_ADDSUB_C)
+  return fe_add_ptx(a, b);
+#endif
   fe r;
   u32 cy = add_n<8>(r.v, a.v, b.v);
   cy = fe_addc_k(r.v, cy);
@@ -177,6 +235,9 @@ EB_HD fe fe_add(const fe& a, const fe& b) {
 }
 
 EB_HD fe fe_sub(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(EB_ADDSUB_C)
+  return fe_sub_ptx(a, b);
+#endif
   fe r;
   u32 bw = sub_n<8>(r.v, a.v, b.v);
   u32 t[8] = {bw ? K256_C0 : 0u, bw, 0, 0, 0, 0, 0, 0};
