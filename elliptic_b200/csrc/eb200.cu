@@ -9,6 +9,7 @@
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
 #include "ecdsa_k256_replay.cuh"
+#include "ecdsa_sw_replay.cuh"
 #include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
@@ -169,6 +170,20 @@ sw_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __res
   if (pre && pre[i]) { status[i] = pre[i]; return; }
   status[i] = SW<C>::verify_item(i, N, pub, r, ws, gtab, qtab);
 }
+// Exact replay of the reference's wNAF schedule for off-curve keys (ecdsa_sw_replay.cuh)
+template <class C>
+__global__ void __launch_bounds__(128) sw_replay_tab_kernel(u32* tab) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < SWReplay<C>::NAF_PTS) SWReplay<C>::tab_entry(t, tab + 2 * C::N * t);
+}
+template <class C>
+__global__ void __launch_bounds__(128)
+sw_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s,
+                 const uint8_t* __restrict__ pub, const u32* __restrict__ tab, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
+  status[i] = SWReplay<C>::verify_item(i, e, r, s, pub, tab);
+}
 template <class C>
 __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint8_t* __restrict__ in, u32 fmt,
                                                             uint8_t* __restrict__ xy, uint8_t* __restrict__ pre) {
@@ -283,6 +298,7 @@ struct Ctx {
   int device = -1;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   u32* gtab[8] = {};
+  u32* sw_replay_tab[8] = {};         // p256/p384: the reference's wnd-8 NAF table of G
   u32* replay_tab = nullptr;          // secp256k1: the reference's wnd-7 NAF table of G and its beta image
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
   uint8_t* d_ws = nullptr; size_t d_ws_cap = 0;
@@ -349,6 +365,9 @@ int sw_ensure_table(int curve) {
   size_t entries = (size_t)W::GWINDOWS * W::GENTRIES;
   CK(cudaMalloc(&g.gtab[curve], entries * 2 * W::N * 4));
   sw_gtab_kernel<C><<<(unsigned)((entries + 127) / 128), 128, 0, g.stream>>>(g.gtab[curve]);
+  CK(cudaGetLastError());
+  CK(cudaMalloc(&g.sw_replay_tab[curve], (size_t)SWReplay<C>::TAB_WORDS * 4));
+  sw_replay_tab_kernel<C><<<1, 128, 0, g.stream>>>(g.sw_replay_tab[curve]);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   return EB200_OK;
@@ -419,11 +438,19 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     CK(cudaGetLastError());
     if (ev_main0) CK(cudaEventRecord(ev_main0, st));
     sw_verify_kernel<P256><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+    CK(cudaGetLastError());
+    if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
+    sw_replay_kernel<P256><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.sw_replay_tab[curve], d_status);
+    cnt++;
   } else {
     sw_prep_kernel<P384><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
     CK(cudaGetLastError());
     if (ev_main0) CK(cudaEventRecord(ev_main0, st));
     sw_verify_kernel<P384><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+    CK(cudaGetLastError());
+    if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
+    sw_replay_kernel<P384><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.sw_replay_tab[curve], d_status);
+    cnt++;
   }
   CK(cudaGetLastError());
   if (ev_main1) CK(cudaEventRecord(ev_main1, st));
@@ -471,6 +498,7 @@ int eb200_init(int device) {
     if (!g.ev_done[i]) CK(cudaEventCreate(&g.ev_done[i]));
   }
   for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  for (int c = 0; c < 8; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
   if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   g.device = device;
   g.ready = true;
@@ -485,6 +513,7 @@ int eb200_shutdown(void) {
   if (!g.ready) return EB200_OK;
   cudaSetDevice(g.device);
   for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  for (int c = 0; c < 8; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
   if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   cudaFree(g.d_in); g.d_in = nullptr; g.d_in_cap = 0;
   cudaFree(g.d_ws); g.d_ws = nullptr; g.d_ws_cap = 0;

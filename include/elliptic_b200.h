@@ -35,9 +35,10 @@ extern "C" {
 #define EB200_ST_TRUE 1                 /* returned true */
 #define EB200_ST_THROW_INVALID_POINT 2  /* threw Error('invalid point')  short.js:195, edwards.js:84 */
 #define EB200_ST_THROW_NOT_VALIDATED 3  /* threw Error('public point not validated')  ec/key.js:104 */
-#define EB200_ST_NEEDS_HOST 4           /* result is not a group-law function of the inputs (off-curve
-                                           un-validated key): caller must run the reference's
-                                           own single-item path for this item */
+#define EB200_ST_NEEDS_HOST 4           /* internal: the fast kernel's flag for an off-curve un-validated key
+                                           (SURVEY 8a Q1).  Every verify entry point re-runs flagged items
+                                           through an exact replay of the reference's own schedule on the GPU,
+                                           so callers never see this value */
 #define EB200_ST_THROW_ASSERT 5         /* threw Error('Assertion failed') (bn.js sqrt / hybrid parity) */
 #define EB200_ST_THROW_POINT_FORMAT 6   /* threw Error('Unknown point format')  base.js:291 */
 #define EB200_ST_INFINITY 7             /* (recover) returned the point at infinity */

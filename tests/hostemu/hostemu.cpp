@@ -196,3 +196,37 @@ extern "C" void he_sign(size_t N, const uint8_t* e, const uint8_t* priv, u32 can
                         uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status) {
   for (size_t i = 0; i < N; i++) status[i] = k256_sign_item(i, e, priv, canonical, gtab, r, s, recid);
 }
+
+// ---------------------------------------------------------------------------
+// exact replay of the reference's non-GLV wNAF schedule (p256 / p384)
+#include "../../elliptic_b200/csrc/ecdsa_sw_replay.cuh"
+template <class C>
+static std::vector<u32>& sw_replay_tab() {
+  static std::vector<u32> tab;
+  if (tab.empty()) {
+    tab.resize(SWReplay<C>::TAB_WORDS);
+    for (int t = 0; t < SWReplay<C>::NAF_PTS; t++) SWReplay<C>::tab_entry(t, &tab[2 * C::N * t]);
+  }
+  return tab;
+}
+template <class C>
+static void sw_replay_jmuladd_host(const u32* u1, const u32* u2, const u32* qx, const u32* qy, u32* xyz) {
+  typedef SWReplay<C> R;
+  typename R::aff Q;
+  typename R::fe t;
+  copy_n<C::N>(t.v, qx); Q.x = R::F::to_mont(t);
+  copy_n<C::N>(t.v, qy); Q.y = R::F::to_mont(t);
+  typename R::jac a = R::jmul_add(u1, u2, Q, sw_replay_tab<C>().data());
+  copy_n<C::N>(xyz, R::F::from_mont(a.x).v);
+  copy_n<C::N>(xyz + C::N, R::F::from_mont(a.y).v);
+  copy_n<C::N>(xyz + 2 * C::N, R::F::from_mont(a.z).v);
+}
+extern "C" void he_sw_replay_jmuladd(int curve, const u32* u1, const u32* u2, const u32* qx, const u32* qy, u32* xyz) {
+  if (curve == 2) sw_replay_jmuladd_host<P256>(u1, u2, qx, qy, xyz);
+  else sw_replay_jmuladd_host<P384>(u1, u2, qx, qy, xyz);
+}
+extern "C" void he_sw_replay_verify(int curve, size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
+  for (size_t i = 0; i < N; i++)
+    status[i] = curve == 2 ? SWReplay<P256>::verify_item(i, e, r, s, pub, sw_replay_tab<P256>().data())
+                           : SWReplay<P384>::verify_item(i, e, r, s, pub, sw_replay_tab<P384>().data());
+}

@@ -34,11 +34,43 @@ def sw_edge_items(ec, ln, seed=5, count=60):
     return items
 
 
-def sw_expected(ec, ln, it):
+def sw_off_curve_items(ec, ln, seed=4, count=12):
+    """Un-validated off-curve keys (ec/key.js:95).  Even items are minted so that the reference's own
+    schedule lands on x(R) == r (verdict TRUE); odd items are random (FALSE)."""
+    n, P = ec.n, ec.curve.p
+    rnd = random.Random(seed)
+    items = []
+    while len(items) < count:
+        x, y = rnd.randrange(P), rnd.randrange(P)
+        if len(items) % 4 == 2: y = 0
+        Q = ec.curve.point(x, y)
+        if ec.curve.validate(Q):
+            continue
+        if len(items) % 2:
+            items.append((rnd.randrange(n), rnd.randrange(1, n), rnd.randrange(1, n), x, y))
+            continue
+        u1, u2 = rnd.randrange(1, n), rnd.randrange(1, n)
+        R = ec.g.jmul_add(u1, Q, u2)
+        if R.z % P == 0:
+            continue
+        zi = pow(R.z, -1, P)
+        r = (R.x * zi * zi % P) % n
+        if r == 0:
+            continue
+        s = r * pow(u2, -1, n) % n
+        e = u1 * s % n
+        # u1, u2 recomputed by verify are the same residues, so the schedule and hence R repeat
+        items.append((e, r, s, x, y))
+    return items
+
+
+def sw_expected(ec, ln, it, replay=True):
+    """replay=False: the fast kernel alone flags off-curve keys 4; the product path (replay=True)
+    re-runs them through the exact-replay kernel and returns the reference's verdict."""
     e, r, s, x, y = it
     n = ec.n
     if not (1 <= r < n and 1 <= s < n):
         return 0
-    if not ec.curve.validate(ec.curve.point(x, y)):
+    if not replay and not ec.curve.validate(ec.curve.point(x, y)):
         return 4
     return int(ec.verify((e if e < n else e - n).to_bytes(ln, "big"), {"r": r, "s": s}, {"x": x, "y": y}))

@@ -91,7 +91,7 @@ def test_sw_verify_pipeline_against_oracle(he, name, cid, ln):
     pub = b"".join(it[3].to_bytes(ln, "big") + it[4].to_bytes(ln, "big") for it in items)
     st = (ctypes.c_uint8 * n)()
     he.he_sw_verify(cid, ctypes.c_size_t(n), col(0), col(1), col(2), pub, st)
-    assert [int(v) for v in st] == [sw_expected(ec, ln, it) for it in items]
+    assert [int(v) for v in st] == [sw_expected(ec, ln, it, replay=False) for it in items]
 
 
 def test_ed25519_and_x25519_bodies_against_oracle(he):
@@ -178,3 +178,51 @@ def test_sign_and_hash_bodies_against_oracle(he):
         assert bytes(o) == hashlib.sha512(msg).digest()
         o = (ctypes.c_uint8 * 32)(); he.he_sha256(msg, ctypes.c_size_t(nbytes), o)
         assert bytes(o) == hashlib.sha256(msg).digest()
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+def test_sw_replay_matches_reference_schedule_point_for_point(he, name, cid, ln):
+    """The off-curve replay (ecdsa_sw_replay.cuh) must land on the same Jacobian triple as the
+    oracle's _wnaf_mul_add, not just the same verdict: the coordinates are compared exactly."""
+    from oracle.ref_py.ec import EC
+    ec = EC(name)
+    n, p, k = ec.n, ec.curve.p, ln // 4
+    rnd = random.Random(9 + cid)
+    cases = []
+    for t in range(10):
+        u1, u2 = rnd.randrange(n), rnd.randrange(n)
+        x, y = rnd.randrange(p), rnd.randrange(p)
+        if t == 0: u1 = 0
+        if t == 1: u2 = 0
+        if t == 2: y = 0
+        if t == 3: x = 0
+        if t == 4: x, y = ec.g.x, ec.g.y
+        if t == 5: u1, u2 = 255, 3
+        if t == 6: x, y, u1, u2 = ec.g.x, p - ec.g.y, 1, 1       # G + (-G)
+        if t == 7: x, y, u1, u2 = ec.g.x, ec.g.y, 1, 1           # G + G through mixedAdd's dbl branch
+        cases.append((u1, u2, x, y))
+    for u1, u2, x, y in cases:
+        ref = ec.g.jmul_add(u1, ec.curve.point(x, y), u2)
+        out = (ctypes.c_uint32 * (3 * k))()
+        he.he_sw_replay_jmuladd(cid, L(u1, k), L(u2, k), L(x, k), L(y, k), out)
+        got = tuple(sum(int(out[c * k + i]) << (32 * i) for i in range(k)) for c in range(3))
+        if ref.z % p == 0:
+            assert got[2] == 0
+        else:
+            assert got == (ref.x % p, ref.y % p, ref.z % p), (u1, u2, x, y)
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+def test_sw_replay_verdicts_for_off_curve_keys(he, name, cid, ln):
+    from oracle.ref_py.ec import EC
+    from sw_items import sw_off_curve_items
+    ec = EC(name)
+    items = sw_off_curve_items(ec, ln, seed=4, count=12)
+    n = len(items)
+    col = lambda k: b"".join(it[k].to_bytes(ln, "big") for it in items)
+    pub = b"".join(it[3].to_bytes(ln, "big") + it[4].to_bytes(ln, "big") for it in items)
+    st = (ctypes.c_uint8 * n)()
+    he.he_sw_replay_verify(cid, ctypes.c_size_t(n), col(0), col(1), col(2), pub, st)
+    exp = [int(ec.verify(it[0].to_bytes(ln, "big"), {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
+    assert [int(v) for v in st] == exp
+    assert 1 in exp and 0 in exp
