@@ -23,7 +23,7 @@ EXPORTS = [
     "eb200_selftest_fe", "eb200_selftest_gtab", "eb200_selftest_gtab_dims",
     "eb200_eddsa_verify_batch", "eb200_eddsa_verify_workspace_bytes", "eb200_eddsa_verify_batch_dev",
     "eb200_x25519_derive_batch", "eb200_x25519_derive_batch_dev", "eb200_ecdsa_recover_batch", "eb200_ecdsa_sign_batch",
-    "eb200_eddsa_verify_batch_msgs",
+    "eb200_eddsa_verify_batch_msgs", "eb200_scalar_mul_batch", "eb200_mul_add_batch",
 ]
 
 
@@ -68,6 +68,8 @@ def load():
     lib.eb200_eddsa_verify_batch_msgs.argtypes = [c.c_size_t] + [c.c_void_p] * 6
     lib.eb200_ecdsa_sign_batch.argtypes = [c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_uint32] + [c.c_void_p] * 4
     lib.eb200_ecdsa_recover_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 6
+    lib.eb200_scalar_mul_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4
+    lib.eb200_mul_add_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 5
     lib.eb200_selftest_gtab_dims.argtypes = [c.c_int] + [c.c_void_p] * 3
     lib.eb200_selftest_fe.argtypes = [c.c_int, c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.eb200_selftest_gtab.argtypes = [c.c_int, c.c_void_p, c.c_size_t]

@@ -91,6 +91,35 @@ k256_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __res
   status[i] = rp_verify_item(i, e, r, s, pub, tab);
 }
 
+// Point.mul / Point.mulAdd batches (short.js:422-441): k1*G + k2*P, k2*P, or k*G
+__global__ void __launch_bounds__(128)
+k256_prep_scalars_kernel(size_t N, const uint8_t* __restrict__ k1, const uint8_t* __restrict__ k2, u32* __restrict__ ws) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) prep_scalars_item(i, N, k1, k2, ws);
+}
+__global__ void __launch_bounds__(EB_VERIFY_BLOCK, EB_VERIFY_MINBLOCKS)
+k256_mul_add_kernel(size_t N, const uint8_t* __restrict__ pts, const u32* __restrict__ ws, const u32* __restrict__ gtab,
+                    u32* __restrict__ qtab, uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = mul_add_item(i, N, pts, ws, gtab, qtab, out);
+}
+__global__ void __launch_bounds__(128)
+k256_mul_add_replay_kernel(size_t N, const uint8_t* __restrict__ k1, const uint8_t* __restrict__ k2,
+                           const uint8_t* __restrict__ pts, const u32* __restrict__ tab, uint8_t* __restrict__ out,
+                           uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
+  status[i] = rp_mul_add_item(i, k1, k2, pts, tab, out);
+}
+__global__ void __launch_bounds__(128)
+k256_mul_g_kernel(size_t N, const uint8_t* __restrict__ k, const u32* __restrict__ gtab, uint8_t* __restrict__ out,
+                  uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = k256_mul_g_item(i, k, gtab, out);
+}
+
 // SEC1 decode (BaseCurve.decodePoint, lib/elliptic/curve/base.js:270-292; pointFromX short.js:187-204)
 // fmt 1: 65-byte 04|06|07 || x || y ; fmt 2: 33-byte 02|03 || x.  Writes x||y (64 B) + a pre-status.
 __global__ void __launch_bounds__(128) k256_decode_pub_kernel(size_t N, const uint8_t* __restrict__ in, u32 fmt,
@@ -687,6 +716,74 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
   cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
   g.timing.launches = 2;
   return EB200_OK;
+}
+
+// ---- Point.mul / Point.mulAdd batches (secp256k1) -----------------------------------------------------
+// k1 == NULL: k2*P;  pts == NULL: k2*G;  both given: k1*G + k2*P.
+static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts,
+                          uint8_t* out_xy, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (n == 0) return EB200_OK;
+  if (!k2 || !out_xy || !status || (k1 && !pts)) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(curve);
+  if (rc) return rc;
+  WsLayout L = ws_layout(curve, n);
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (2 * 32 + 64 + 64) + 256))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, L.total))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  uint8_t *d_k1 = g.d_in, *d_k2 = d_k1 + 32 * n, *d_pts = d_k2 + 32 * n, *d_out = d_pts + 64 * n;
+  cudaStream_t st = g.stream;
+  unsigned nb = (unsigned)((n + 127) / 128), launches = 0;
+  CK(cudaEventRecord(g.ev[0], st));
+  if (k1) CK(cudaMemcpyAsync(d_k1, k1, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_k2, k2, 32 * n, cudaMemcpyHostToDevice, st));
+  if (pts) CK(cudaMemcpyAsync(d_pts, pts, 64 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  if (!pts) {
+    CK(cudaEventRecord(g.ev[4], st));
+    k256_mul_g_kernel<<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[5], st));
+    launches = 1;
+  } else {
+    k256_prep_scalars_kernel<<<nb, 128, 0, st>>>(n, k1 ? d_k1 : nullptr, d_k2, (u32*)(g.d_ws + L.ws));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[4], st));
+    k256_mul_add_kernel<<<(unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK), EB_VERIFY_BLOCK, 0, st>>>(
+        n, d_pts, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[5], st));
+    k256_mul_add_replay_kernel<<<nb, 128, 0, st>>>(n, k1 ? d_k1 : nullptr, d_k2, d_pts, g.replay_tab, d_out, g.d_status);
+    CK(cudaGetLastError());
+    launches = 3;
+  }
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(out_xy, d_out, 64 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
+  g.timing.launches = launches;
+  return EB200_OK;
+}
+
+int eb200_scalar_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* points_xy, uint8_t* out_xy,
+                           uint8_t* status) {
+  return mul_add_common(curve, n, nullptr, k, points_xy, out_xy, status);
+}
+
+int eb200_mul_add_batch(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* p2_xy,
+                        uint8_t* out_xy, uint8_t* status) {
+  if (n && (!k1 || !p2_xy)) return EB200_ERR_ARG;
+  return mul_add_common(curve, n, k1, k2, p2_xy, out_xy, status);
 }
 
 // ---- ECDSA sign (secp256k1, RFC 6979 nonces on the GPU) -------------------------------------------------

@@ -36,9 +36,9 @@ enum : uint8_t {
 // workspace layout (SoA, word-major so lanes are coalesced): PREP_WORDS words per item
 //   [0..7]  mG = (u1' - 1)/2 where u1' = u1 or n-u1 made odd (8 limbs)
 //   [8..12] m1 = (|k1|-1)/2, [13..17] m2 = (|k2|-1)/2
-//   [18]    flags: bit0 sig invalid (-> FALSE), bit1 negG, bit2 neg1, bit3 neg2
+//   [18]    flags: bit0 sig invalid (-> FALSE), bit1 negG, bit2 neg1, bit3 neg2, bit4 no base-point term
 constexpr int PREP_WORDS = 19;
-constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG1 = 4, FL_NEG2 = 8;
+constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG1 = 4, FL_NEG2 = 8, FL_NOG = 16;
 constexpr int PREP_BATCH = 16;          // items per thread in the batched inversion
 constexpr int QTAB_ENTRIES = 8;         // odd multiples 1,3,..,15
 constexpr int QTAB_WORDS = QTAB_ENTRIES * 24;  // per item: (x, y, beta*x) x 8
@@ -112,6 +112,32 @@ EB_HD void gtab_entry(int j, int idx, u32* out16) {
   for (int i = 0; i < 8; i++) { out16[i] = r.x.v[i]; out16[8 + i] = r.y.v[i]; }
 }
 
+// Recode (u1, u2) for k256_dsm and store them SoA: u1 odd-ified for the fixed-base windows, u2 GLV-split
+// into odd halves.
+EB_HD void prep_store(size_t i, size_t N, u32* u1, const u32* u2, u32 flags, u32* ws) {
+  u32 nn[8];
+  K256N::n(nn);
+  // u1 odd-ify: u1' = n - u1 when u1 is even (then the G part is negated)
+  if ((u1[0] & 1) == 0) {
+    sub_n<8>(u1, nn, u1);
+    flags |= FL_NEGG;
+  }
+  u32 m1[5], m2[5];
+  bool n1, n2;
+  glv_split_odd(u2, m1, &n1, m2, &n2);
+  if (n1) flags |= FL_NEG1;
+  if (n2) flags |= FL_NEG2;
+  for (int w = 0; w < 8; w++) {
+    u32 hi = (w < 7) ? u1[w + 1] : 0;
+    ws[(size_t)w * N + i] = (u1[w] >> 1) | (hi << 31);
+  }
+  for (int w = 0; w < 5; w++) {
+    ws[(size_t)(8 + w) * N + i] = m1[w];
+    ws[(size_t)(13 + w) * N + i] = m2[w];
+  }
+  ws[(size_t)18 * N + i] = flags;
+}
+
 // ---------------------------------------------------------------------------
 // prep: thread `tid` of `T` handles items tid, tid+T, ... (up to PREP_BATCH).
 // e, r, s: N x 32 bytes big-endian.  ws: PREP_WORDS x N words.
@@ -178,26 +204,26 @@ EB_HD void prep_thread(size_t tid, size_t T, size_t N, const uint8_t* e, const u
       sc_mont_mul(u1, ev, sinv);      // e * s^-1 mod n   (ec/index.js:206)
       sc_mont_mul(u2, rv, sinv);      // r * s^-1 mod n   (ec/index.js:207)
     }
-    // u1 odd-ify: u1' = n - u1 when u1 is even (then the G part is negated)
-    if ((u1[0] & 1) == 0) {
-      sub_n<8>(u1, nn, u1);
-      flags |= FL_NEGG;
-    }
-    u32 m1[5], m2[5];
-    bool n1, n2;
-    glv_split_odd(u2, m1, &n1, m2, &n2);
-    if (n1) flags |= FL_NEG1;
-    if (n2) flags |= FL_NEG2;
-    for (int w = 0; w < 8; w++) {
-      u32 hi = (w < 7) ? u1[w + 1] : 0;
-      ws[(size_t)w * N + i] = (u1[w] >> 1) | (hi << 31);
-    }
-    for (int w = 0; w < 5; w++) {
-      ws[(size_t)(8 + w) * N + i] = m1[w];
-      ws[(size_t)(13 + w) * N + i] = m2[w];
-    }
-    ws[(size_t)18 * N + i] = flags;
+    prep_store(i, N, u1, u2, flags, ws);
   }
+}
+
+// Generic scalars for BasePoint.mul / mulAdd callers (short.js:422-441): k1, k2 are any 256-bit
+// integers (big-endian), reduced mod n here (the group law only sees the residue for on-curve
+// points).  k1 == nullptr: no base-point term.
+EB_HD void prep_scalars_item(size_t i, size_t N, const uint8_t* k1, const uint8_t* k2, u32* ws) {
+  u32 nn[8], u1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, u2[8];
+  K256N::n(nn);
+  u32 flags = 0;
+  if (k1) {
+    load_be<8>(u1, k1 + 32 * i);
+    if (geq_n<8>(u1, nn)) sub_n<8>(u1, u1, nn);
+  } else {
+    flags |= FL_NOG;
+  }
+  load_be<8>(u2, k2 + 32 * i);
+  if (geq_n<8>(u2, nn)) sub_n<8>(u2, u2, nn);
+  prep_store(i, N, u1, u2, flags, ws);
 }
 
 // ---------------------------------------------------------------------------
@@ -271,6 +297,7 @@ EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32*
   acc.z = fe_mul(acc.z, zglobal);
 
   // ---- u1*G from the fixed table: GTAB_WINDOWS windows of GTAB_W bits, regular signed-odd digits
+  if (flags & FL_NOG) return acc;             // Point.mul: no base-point term (uniform across a batch)
   for (int j = 0; j < GTAB_WINDOWS; j++) {
     const int pos = GTAB_W * j;
     u32 lo = ws[(size_t)(pos >> 5) * N + i];
@@ -338,6 +365,26 @@ EB_HD uint8_t recover_item(size_t i, size_t N, const uint8_t* r, const uint8_t* 
   ge_aff R; R.x = x; R.y = y;
   u32 flags = ws[(size_t)18 * N + i];
   ge_jac acc = k256_dsm(i, N, R, flags, ws, gtab, qtab);
+  if (fe_is_zero(acc.z)) return ST_INFINITY;
+  ge_aff q = jac_to_aff(acc);
+  fe qx = fe_normalize(q.x), qy = fe_normalize(q.y);
+  store_be<8>(out + 64 * i, qx.v);
+  store_be<8>(out + 64 * i + 32, qy.v);
+  return ST_TRUE;
+}
+
+// BasePoint.mul / Point.mulAdd (short.js:422-441) for an on-curve point: k1*G + k2*P (or k2*P alone), affine
+// result as Point.toP / JPoint.toP (short.js:516-526).  ST_TRUE = point written, ST_INFINITY = the point at
+// infinity (out zeroed), ST_NEEDS_HOST = P is off the curve (the replay kernel re-runs it).
+EB_HD uint8_t mul_add_item(size_t i, size_t N, const uint8_t* pts, const u32* ws, const u32* gtab, u32* qtab,
+                           uint8_t* out) {
+  for (int b = 0; b < 64; b++) out[64 * i + b] = 0;
+  ge_aff P;
+  P.x = fe_from_be(pts + 64 * i);
+  P.y = fe_from_be(pts + 64 * i + 32);
+  if (!aff_on_curve(P)) return ST_NEEDS_HOST;
+  u32 flags = ws[(size_t)18 * N + i];
+  ge_jac acc = k256_dsm(i, N, P, flags, ws, gtab, qtab);
   if (fe_is_zero(acc.z)) return ST_INFINITY;
   ge_aff q = jac_to_aff(acc);
   fe qx = fe_normalize(q.x), qy = fe_normalize(q.y);

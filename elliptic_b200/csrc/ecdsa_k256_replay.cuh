@@ -187,10 +187,11 @@ struct rp_any { bool is_j; rp_aff a; ge_jac j; };
 
 // g.jmulAdd(u1, Q, u2) exactly as the reference computes it; returns the Jacobian result.
 // tab: REPLAY_TAB_WORDS words: (2i+1)G, i < 128, then their beta images (canonical x||y limbs).
+// u1 == nullptr: Q.mul(u2) = _endoWnafMulAdd([Q], [u2]) (short.js:428-429), i.e. the JSF comb alone.
 EB_HD ge_jac rp_jmul_add(const u32* u1, const u32* u2, const fe& qx, const fe& qy, const u32* tab) {
   u32 k1g[8], k2g[8], k1q[8], k2q[8];
-  bool ng, nbg, nq, nbq;
-  rp_endo_split(u1, k1g, &ng, k2g, &nbg);
+  bool ng = false, nbg = false, nq, nbq;
+  if (u1) rp_endo_split(u1, k1g, &ng, k2g, &nbg);
   rp_endo_split(u2, k1q, &nq, k2q, &nbq);
   rp_aff Qp; Qp.x = fe_normalize(qx); Qp.y = fe_normalize(qy); Qp.inf = false;
   rp_aff Qb = Qp;
@@ -218,8 +219,8 @@ EB_HD ge_jac rp_jmul_add(const u32* u1, const u32* u2, const fe& qx, const fe& q
   int max = rp_get_jsf(j1, j2, k1q, k2q);
   for (int j = 0; j < max; j++) nqd[j] = INDEX[(j1[j] + 1) * 3 + (j2[j] + 1)];
   int lq = max;
-  int lg = rp_get_naf(ngd, k1g, REPLAY_NAF_W, 256);
-  int lbg = rp_get_naf(nbgd, k2g, REPLAY_NAF_W, 256);
+  int lg = u1 ? rp_get_naf(ngd, k1g, REPLAY_NAF_W, 256) : 0;
+  int lbg = u1 ? rp_get_naf(nbgd, k2g, REPLAY_NAF_W, 256) : 0;
   if (lg > max) max = lg;
   if (lbg > max) max = lbg;
   ge_jac acc = jac_infinity();
@@ -287,6 +288,25 @@ EB_HD uint8_t rp_verify_item(size_t i, const uint8_t* e, const uint8_t* r, const
     if (fe_eq(acc.x, fe_mul(rn, z2))) return 1;
   }
   return 0;
+}
+
+// Point.mulAdd / Point.mul for an off-curve point (the constructor never validates, short.js:251-271):
+// same schedule, then JPoint.toP (short.js:516-526).  Scalars are used as given (no reduction mod n), as
+// the reference does.  k1 == nullptr: P.mul(k2).
+EB_HD uint8_t rp_mul_add_item(size_t i, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, const u32* tab,
+                              uint8_t* out) {
+  u32 u1[8], u2[8];
+  if (k1) load_be<8>(u1, k1 + 32 * i);
+  load_be<8>(u2, k2 + 32 * i);
+  fe px = fe_from_be(pts + 64 * i), py = fe_from_be(pts + 64 * i + 32);
+  ge_jac acc = rp_jmul_add(k1 ? u1 : nullptr, u2, px, py, tab);
+  for (int b = 0; b < 64; b++) out[64 * i + b] = 0;
+  if (fe_is_zero(acc.z)) return ST_INFINITY;
+  ge_aff q = jac_to_aff(acc);
+  fe qx = fe_normalize(q.x), qy = fe_normalize(q.y);
+  store_be<8>(out + 64 * i, qx.v);
+  store_be<8>(out + 64 * i + 32, qy.v);
+  return ST_TRUE;
 }
 
 // table builder: entry t < 128: (2t+1)G ; t >= 128: (beta*x, y) of entry t-128

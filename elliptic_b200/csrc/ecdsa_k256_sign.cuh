@@ -97,6 +97,20 @@ EB_HD ge_aff k256_mul_g(const u32* k, const u32* gtab) {
   return r;
 }
 
+// G.mul(k) (short.js:422-427 -> _fixedNafMul, base.js:52-84) for any 256-bit k: affine x||y, or infinity.
+EB_HD uint8_t k256_mul_g_item(size_t i, const uint8_t* k, const u32* gtab, uint8_t* out) {
+  u32 nn[8], kv[8];
+  K256N::n(nn);
+  load_be<8>(kv, k + 32 * i);
+  if (geq_n<8>(kv, nn)) sub_n<8>(kv, kv, nn);
+  for (int b = 0; b < 64; b++) out[64 * i + b] = 0;
+  if (is_zero_n<8>(kv)) return ST_INFINITY;
+  ge_aff r = k256_mul_g(kv, gtab);
+  store_be<8>(out + 64 * i, r.x.v);
+  store_be<8>(out + 64 * i + 32, r.y.v);
+  return ST_TRUE;
+}
+
 // One signature.  e: _truncateToN(msg) (32 bytes BE, < n); priv: the key pair's private scalar
 // (32 bytes BE, already reduced mod n, ec/key.js:76-82).  Writes r, s (32 B BE) and the recovery param.
 EB_HD uint8_t k256_sign_item(size_t i, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,

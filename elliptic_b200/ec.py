@@ -329,6 +329,55 @@ class EC:
             return pts[0]
         raise EllipticError(_THROW_MSG.get(int(st[0]), "status %d" % int(st[0])))
 
+    # ---- curve.point(...).mul / mulAdd batches (short.js:422-441) ---------------------------------------------
+    def _scalars(self, ks):
+        out = np.zeros((len(ks), 32), np.uint8)
+        for i, k in enumerate(ks):
+            k = _bn(k)
+            if k < 0:
+                raise EllipticError("negative scalars are not supported by the batch path")
+            if k >> 256:
+                k %= self.n          # same point for every on-curve input
+            out[i] = np.frombuffer(k.to_bytes(32, "big"), np.uint8)
+        return out
+
+    def _points(self, pts):
+        """curve.point(x, y) (short.js:251-271): coordinates reduced mod p, not validated."""
+        out = np.zeros((len(pts), 64), np.uint8)
+        for i, pt in enumerate(pts):
+            x, y = (pt["x"], pt["y"]) if isinstance(pt, dict) else pt
+            out[i, :32] = np.frombuffer((_bn(x) % self._c["p"]).to_bytes(32, "big"), np.uint8)
+            out[i, 32:] = np.frombuffer((_bn(y) % self._c["p"]).to_bytes(32, "big"), np.uint8)
+        return out
+
+    def _mul_common(self, k1, k2, pts):
+        if self.name != "secp256k1":
+            raise EllipticError("mul/mulAdd batches: only secp256k1 is accelerated")
+        lib = nat.init(self._device)
+        n = len(k2)
+        out = np.zeros((n, 64), np.uint8)
+        st = np.zeros(n, np.uint8)
+        if k1 is None:
+            nat.check(lib.eb200_scalar_mul_batch(self._c["id"], n, k2.ctypes.data, pts.ctypes.data if pts is not None else None,
+                                                 out.ctypes.data, st.ctypes.data))
+        else:
+            nat.check(lib.eb200_mul_add_batch(self._c["id"], n, k1.ctypes.data, k2.ctypes.data, pts.ctypes.data,
+                                              out.ctypes.data, st.ctypes.data))
+        return [(int.from_bytes(out[i, :32].tobytes(), "big"), int.from_bytes(out[i, 32:].tobytes(), "big"))
+                if st[i] == nat.ST_TRUE else None for i in range(n)]
+
+    def g_mul_batch(self, ks):
+        """[G.mul(k) for k in ks] (short.js:422-427, the keygen product ec/key.js:55-60): (x, y) or None = infinity."""
+        return self._mul_common(None, self._scalars(ks), None)
+
+    def mul_batch(self, points, ks):
+        """[curve.point(x, y).mul(k)] (short.js:422-432): (x, y) or None = infinity."""
+        return self._mul_common(None, self._scalars(ks), self._points(points))
+
+    def mul_add_batch(self, k1s, p2s, k2s):
+        """[G.mulAdd(k1, P2, k2)] (short.js:434-441): (x, y) or None = infinity."""
+        return self._mul_common(self._scalars(k1s), self._scalars(k2s), self._points(p2s))
+
     def _signature_enc(self, sig, enc):
         """new Signature(sig, enc) as recoverPubKey calls it (enc passed through, ec/index.js:233)."""
         if isinstance(sig, dict) or (hasattr(sig, "r") and hasattr(sig, "s")):

@@ -230,3 +230,18 @@ extern "C" void he_sw_replay_verify(int curve, size_t N, const uint8_t* e, const
     status[i] = curve == 2 ? SWReplay<P256>::verify_item(i, e, r, s, pub, sw_replay_tab<P256>().data())
                            : SWReplay<P384>::verify_item(i, e, r, s, pub, sw_replay_tab<P384>().data());
 }
+
+// ---------------------------------------------------------------------------
+// Point.mul / mulAdd bodies (secp256k1): fast path + exact replay
+extern "C" void he_mul_add(size_t N, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, const u32* gtab,
+                           uint8_t* out, uint8_t* status) {
+  std::vector<u32> ws((size_t)PREP_WORDS * N), qtab((size_t)QTAB_WORDS * N);
+  for (size_t i = 0; i < N; i++) prep_scalars_item(i, N, k1, k2, ws.data());
+  for (size_t i = 0; i < N; i++) {
+    status[i] = mul_add_item(i, N, pts, ws.data(), gtab, qtab.data(), out);
+    if (status[i] == ST_NEEDS_HOST) status[i] = rp_mul_add_item(i, k1, k2, pts, replay_tab().data(), out);
+  }
+}
+extern "C" void he_mul_g(size_t N, const uint8_t* k, const u32* gtab, uint8_t* out, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = k256_mul_g_item(i, k, gtab, out);
+}

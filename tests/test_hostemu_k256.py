@@ -226,3 +226,57 @@ def test_sw_replay_verdicts_for_off_curve_keys(he, name, cid, ln):
     exp = [int(ec.verify(it[0].to_bytes(ln, "big"), {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
     assert [int(v) for v in st] == exp
     assert 1 in exp and 0 in exp
+
+
+def mul_cases(ec, seed=3):
+    """(k1, k2, x, y) for Point.mul / mulAdd: ordinary, oversize, zero and cancelling scalars, P = +-G,
+    off-curve points (short.js:251-271 never validates)."""
+    rnd = random.Random(seed)
+    n, p, G = ec.n, ec.curve.p, ec.g
+    P1 = G.mul(rnd.randrange(1, n))
+    cases = []
+    for t in range(8):
+        cases.append((rnd.randrange(n), rnd.randrange(n), P1.x, P1.y))
+    d = rnd.randrange(1, n)
+    Pd = G.mul(d)
+    cases += [
+        (0, 5, P1.x, P1.y), (7, 0, P1.x, P1.y), (0, 0, P1.x, P1.y),
+        (n + 3, 2**256 - 1, P1.x, P1.y),                       # not reduced by the reference
+        ((n - d * 9 % n) % n, 9, Pd.x, Pd.y),                  # k1*G + k2*P = O
+        (5, 1, G.x, G.y), (5, n - 5, G.x, G.y), (1, 1, G.x, p - G.y),
+        (rnd.randrange(n), rnd.randrange(n), rnd.randrange(p), rnd.randrange(p)),     # off-curve
+        (rnd.randrange(n), rnd.randrange(n), 0, 0),
+        (3, 2**256 - 5, rnd.randrange(p), rnd.randrange(p)),
+    ]
+    return cases
+
+
+def test_mul_and_mul_add_bodies_against_oracle(he):
+    from oracle.ref_py.ec import EC
+    ec = EC("secp256k1")
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    he.he_gtab_dims(ctypes.byref(W), ctypes.byref(E), ctypes.byref(B))
+    gtab = np.zeros(W.value * E.value * 16, np.uint32)
+    he.he_gtab_fast(gtab.ctypes.data_as(ctypes.c_void_p))
+    gp = gtab.ctypes.data_as(ctypes.c_void_p)
+    cases = mul_cases(ec)
+    n = len(cases)
+    k1 = b"".join(c[0].to_bytes(32, "big") for c in cases)
+    k2 = b"".join(c[1].to_bytes(32, "big") for c in cases)
+    pts = b"".join(c[2].to_bytes(32, "big") + c[3].to_bytes(32, "big") for c in cases)
+
+    def unpack(out, st):
+        return [(int.from_bytes(bytes(out[64 * i:64 * i + 32]), "big"), int.from_bytes(bytes(out[64 * i + 32:64 * i + 64]), "big"))
+                if st[i] == 1 else None for i in range(n)]
+
+    def ref(pt):
+        return None if pt.is_infinity() else (pt.get_x(), pt.get_y())
+
+    out = (ctypes.c_uint8 * (64 * n))(); st = (ctypes.c_uint8 * n)()
+    he.he_mul_add(ctypes.c_size_t(n), k1, k2, pts, gp, out, st)
+    assert unpack(out, st) == [ref(ec.g.mul_add(c[0], ec.curve.point(c[2], c[3]), c[1])) for c in cases]
+    assert set(st) == {1, 7}
+    he.he_mul_add(ctypes.c_size_t(n), None, k2, pts, gp, out, st)
+    assert unpack(out, st) == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
+    he.he_mul_g(ctypes.c_size_t(n), k2, gp, out, st)
+    assert unpack(out, st) == [ref(ec.g.mul(c[1])) for c in cases]
