@@ -14,7 +14,7 @@ from elliptic_b200.ec import EC
 from elliptic_b200.eddsa import EDDSA
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "ed25519_msgs", "curve25519", "k256_sign", "k256_recover"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "ed25519_msgs", "curve25519", "k256_sign", "k256_recover", "k256_mul", "k256_mul_add", "k256_mul_g"]
 CACHE = "/tmp/eb200_cache"
 res = {}
 for name in which:
@@ -53,6 +53,22 @@ for name in which:
                 nat.check(lib.eb200_ecdsa_recover_batch(1, n, ds0["e"].ctypes.data, ds0["r"].ctypes.data, ds0["s"].ctypes.data,
                                                         rid.ctypes.data, out.ctypes.data, st.ctypes.data))
                 return np.where((st == 1) | (st == 2), 1, st).astype(np.uint8)
+    elif name in ("k256_mul", "k256_mul_add", "k256_mul_g"):
+        ds0 = benchdata.gen_ecdsa_verify("secp256k1", n, seed=0xE1110002, cache_dir=CACHE)
+        lib = nat.init(0)
+        out = np.zeros((n, 64), np.uint8)
+        st = np.zeros(n, np.uint8)
+        ds = {"expected": np.ones(n, np.uint8)}
+        k1, k2, pts = ds0["e"], ds0["r"], ds0["pub"]      # any 256-bit scalars; the public keys are on-curve points
+
+        def run():
+            if name == "k256_mul":
+                nat.check(lib.eb200_scalar_mul_batch(1, n, k2.ctypes.data, pts.ctypes.data, out.ctypes.data, st.ctypes.data))
+            elif name == "k256_mul_g":
+                nat.check(lib.eb200_scalar_mul_batch(1, n, k2.ctypes.data, None, out.ctypes.data, st.ctypes.data))
+            else:
+                nat.check(lib.eb200_mul_add_batch(1, n, k1.ctypes.data, k2.ctypes.data, pts.ctypes.data, out.ctypes.data, st.ctypes.data))
+            return st
     else:
         ds = benchdata.gen_x25519_derive(n, cache_dir=CACHE)
         lib = nat.init(0)
