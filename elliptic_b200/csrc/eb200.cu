@@ -213,6 +213,38 @@ sw_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restr
   if (i >= N || status[i] != ST_NEEDS_HOST) return;
   status[i] = SWReplay<C>::verify_item(i, e, r, s, pub, tab);
 }
+// Point.mul / mulAdd batches on the non-GLV short curves
+template <class C>
+__global__ void __launch_bounds__(128)
+sw_prep_scalars_kernel(size_t N, const uint8_t* __restrict__ k1, const uint8_t* __restrict__ k2, u32* __restrict__ ws) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) SW<C>::prep_scalars_item(i, N, k1, k2, ws);
+}
+template <class C>
+__global__ void __launch_bounds__(128, 2)
+sw_mul_add_kernel(size_t N, const uint8_t* __restrict__ pts, const u32* __restrict__ ws, const u32* __restrict__ gtab,
+                  u32* __restrict__ qtab, uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = SW<C>::mul_add_item(i, N, pts, ws, gtab, qtab, out);
+}
+template <class C>
+__global__ void __launch_bounds__(128)
+sw_mul_add_replay_kernel(size_t N, const uint8_t* __restrict__ k1, const uint8_t* __restrict__ k2,
+                         const uint8_t* __restrict__ pts, const u32* __restrict__ tab, uint8_t* __restrict__ out,
+                         uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
+  status[i] = SWReplay<C>::mul_add_item(i, k1, k2, pts, tab, out);
+}
+template <class C>
+__global__ void __launch_bounds__(128)
+sw_mul_g_kernel(size_t N, const uint8_t* __restrict__ k, const u32* __restrict__ gtab, uint8_t* __restrict__ out,
+                uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = SW<C>::mul_g_item(i, k, gtab, out);
+}
 template <class C>
 __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint8_t* __restrict__ in, u32 fmt,
                                                             uint8_t* __restrict__ xy, uint8_t* __restrict__ pre) {
@@ -720,29 +752,60 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
 
 // ---- Point.mul / Point.mulAdd batches (secp256k1) -----------------------------------------------------
 // k1 == NULL: k2*P;  pts == NULL: k2*G;  both given: k1*G + k2*P.
+}  // extern "C"
+
+template <class C>
+static int sw_mul_add_launch(int curve, size_t n, const uint8_t* d_k1, const uint8_t* d_k2, const uint8_t* d_pts,
+                             uint8_t* d_out, const WsLayout& L, cudaStream_t st, unsigned* launches) {
+  unsigned nb = (unsigned)((n + 127) / 128);
+  if (!d_pts) {
+    CK(cudaEventRecord(g.ev[4], st));
+    sw_mul_g_kernel<C><<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[5], st));
+    *launches = 1;
+    return EB200_OK;
+  }
+  sw_prep_scalars_kernel<C><<<nb, 128, 0, st>>>(n, d_k1, d_k2, (u32*)(g.d_ws + L.ws));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[4], st));
+  sw_mul_add_kernel<C><<<nb, 128, 0, st>>>(n, d_pts, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  sw_mul_add_replay_kernel<C><<<nb, 128, 0, st>>>(n, d_k1, d_k2, d_pts, g.sw_replay_tab[curve], d_out, g.d_status);
+  CK(cudaGetLastError());
+  *launches = 3;
+  return EB200_OK;
+}
+
 static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts,
                           uint8_t* out_xy, uint8_t* status) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   if (!k2 || !out_xy || !status || (k1 && !pts)) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
   int rc = ensure_table(curve);
   if (rc) return rc;
+  const size_t len = curve_len(curve);
   WsLayout L = ws_layout(curve, n);
-  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (2 * 32 + 64 + 64) + 256))) return rc;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * 6 * len + 256))) return rc;
   if ((rc = grow(&g.d_ws, &g.d_ws_cap, L.total))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
-  uint8_t *d_k1 = g.d_in, *d_k2 = d_k1 + 32 * n, *d_pts = d_k2 + 32 * n, *d_out = d_pts + 64 * n;
+  uint8_t *d_k1 = g.d_in, *d_k2 = d_k1 + len * n, *d_pts = d_k2 + len * n, *d_out = d_pts + 2 * len * n;
   cudaStream_t st = g.stream;
   unsigned nb = (unsigned)((n + 127) / 128), launches = 0;
   CK(cudaEventRecord(g.ev[0], st));
-  if (k1) CK(cudaMemcpyAsync(d_k1, k1, 32 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_k2, k2, 32 * n, cudaMemcpyHostToDevice, st));
-  if (pts) CK(cudaMemcpyAsync(d_pts, pts, 64 * n, cudaMemcpyHostToDevice, st));
+  if (k1) CK(cudaMemcpyAsync(d_k1, k1, len * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_k2, k2, len * n, cudaMemcpyHostToDevice, st));
+  if (pts) CK(cudaMemcpyAsync(d_pts, pts, 2 * len * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
-  if (!pts) {
+  if (curve == EB200_CURVE_P256) {
+    if ((rc = sw_mul_add_launch<P256>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches))) return rc;
+  } else if (curve == EB200_CURVE_P384) {
+    if ((rc = sw_mul_add_launch<P384>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches))) return rc;
+  } else if (!pts) {
     CK(cudaEventRecord(g.ev[4], st));
     k256_mul_g_kernel<<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
     CK(cudaGetLastError());
@@ -761,7 +824,7 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
     launches = 3;
   }
   CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(out_xy, d_out, 64 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_xy, d_out, 2 * len * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(g.ev[3], st));
   CK(cudaStreamSynchronize(st));
@@ -774,6 +837,8 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
   g.timing.launches = launches;
   return EB200_OK;
 }
+
+extern "C" {
 
 int eb200_scalar_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* points_xy, uint8_t* out_xy,
                            uint8_t* status) {

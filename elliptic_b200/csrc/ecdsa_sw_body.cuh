@@ -32,7 +32,7 @@ struct SW {
   static constexpr int PREP_WORDS = 2 * N + 1;               // mG[N], m2[N], flags
   static constexpr int QTAB_WORDS = 8 * 3 * N;               // 8 Jacobian entries
   static constexpr int BATCH = 16;
-  static constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG2 = 4;
+  static constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG2 = 4, FL_NOG = 8;
 
   static EB_HD jac infinity() { jac r; r.x = F::one(); r.y = F::one(); r.z = F::zero(); return r; }
   static EB_HD jac from_aff(const aff& p) { jac r; r.x = p.x; r.y = p.y; r.z = F::one(); return r; }
@@ -182,15 +182,37 @@ struct SW {
       load_be<N>(ev.v, e + LEN * i);
       sc u1 = S::mul(ev, sinv);     // plain e * Montgomery s^-1 -> plain   (ec/index.js:206)
       sc u2 = S::mul(rv, sinv);     //                                        (ec/index.js:207)
-      if ((u1.v[0] & 1) == 0) { sub_n<N>(u1.v, nmod, u1.v); flags |= FL_NEGG; }
-      if ((u2.v[0] & 1) == 0) { sub_n<N>(u2.v, nmod, u2.v); flags |= FL_NEG2; }
-      for (int w = 0; w < N; w++) {
-        u32 h1 = (w < N - 1) ? u1.v[w + 1] : 0, h2 = (w < N - 1) ? u2.v[w + 1] : 0;
-        ws[(size_t)w * cnt_items + i] = (u1.v[w] >> 1) | (h1 << 31);
-        ws[(size_t)(N + w) * cnt_items + i] = (u2.v[w] >> 1) | (h2 << 31);
-      }
-      ws[(size_t)(2 * N) * cnt_items + i] = flags;
+      prep_store(i, cnt_items, u1.v, u2.v, flags, ws);
     }
+  }
+
+  // odd-ify and store (u1, u2) SoA for dsm()
+  static EB_HD void prep_store(size_t i, size_t cnt_items, u32* u1, u32* u2, u32 flags, u32* ws) {
+    u32 nmod[N];
+    n_limbs(nmod);
+    if ((u1[0] & 1) == 0) { sub_n<N>(u1, nmod, u1); flags |= FL_NEGG; }
+    if ((u2[0] & 1) == 0) { sub_n<N>(u2, nmod, u2); flags |= FL_NEG2; }
+    for (int w = 0; w < N; w++) {
+      u32 h1 = (w < N - 1) ? u1[w + 1] : 0, h2 = (w < N - 1) ? u2[w + 1] : 0;
+      ws[(size_t)w * cnt_items + i] = (u1[w] >> 1) | (h1 << 31);
+      ws[(size_t)(N + w) * cnt_items + i] = (u2[w] >> 1) | (h2 << 31);
+    }
+    ws[(size_t)(2 * N) * cnt_items + i] = flags;
+  }
+
+  // Point.mul / mulAdd callers (short.js:422-441): k1, k2 any integers below 2^(32N), reduced mod n here
+  // (for an on-curve point only the residue matters).  k1 == nullptr: no base-point term.
+  static EB_HD void prep_scalars_item(size_t i, size_t cnt_items, const uint8_t* k1, const uint8_t* k2, u32* ws) {
+    const size_t LEN = 4 * N;
+    u32 nmod[N], u1[N], u2[N];
+    n_limbs(nmod);
+    u32 flags = 0;
+    for (int w = 0; w < N; w++) u1[w] = 0;
+    if (k1) { load_be<N>(u1, k1 + LEN * i); if (geq_n<N>(u1, nmod)) sub_n<N>(u1, u1, nmod); }
+    else flags |= FL_NOG;
+    load_be<N>(u2, k2 + LEN * i);
+    if (geq_n<N>(u2, nmod)) sub_n<N>(u2, u2, nmod);
+    prep_store(i, cnt_items, u1, u2, flags, ws);
   }
 
   static EB_HD void n_limbs(u32* r) { S::Params::mod(r); }
@@ -203,20 +225,8 @@ struct SW {
     return (u32)(both >> (pos & 31)) & ((1u << width) - 1);
   }
 
-  // ---- main: one signature
-  static EB_HD uint8_t verify_item(size_t i, size_t cnt_items, const uint8_t* pub, const uint8_t* r,
-                                   const u32* ws, const u32* gtab, u32* qtab) {
-    const size_t LEN = 4 * N;
-    u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
-    if (flags & FL_INVALID) return 0;   // ST_FALSE
-    aff Q;
-    {
-      fe t;
-      load_be<N>(t.v, pub + 2 * LEN * i);       Q.x = F::to_mont(t);
-      load_be<N>(t.v, pub + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
-    }
-    if (!on_curve(Q)) return 4;          // ST_NEEDS_HOST (un-validated off-curve key, SURVEY 8a Q1)
-
+  // ---- u1*G + u2*Q for an on-curve Q, scalars as stored by prep_store.  Jacobian result.
+  static EB_HD jac dsm(size_t i, size_t cnt_items, const aff& Q, u32 flags, const u32* ws, const u32* gtab, u32* qtab) {
     u32* tab = qtab + (size_t)i * QTAB_WORDS;
     {
       jac P = from_aff(Q);
@@ -244,6 +254,7 @@ struct SW {
       if (w == QWINDOWS - 1) acc = P;
       else acc = add(acc, P);
     }
+    if (flags & FL_NOG) return acc;      // Point.mul: no base-point term
     for (int j = 0; j < GWINDOWS; j++) {
       u32 chunk = extract(ws, cnt_items, i, 0, GW * j, GW);
       const u32 half = 1u << (GW - 1);
@@ -257,6 +268,33 @@ struct SW {
       P.y = F::cmov(P.y, F::neg(P.y), neg);
       acc = madd(acc, P);
     }
+    return acc;
+  }
+
+  static EB_HD aff load_point(const uint8_t* pts, size_t i) {
+    const size_t LEN = 4 * N;
+    aff Q;
+    fe t;
+    load_be<N>(t.v, pts + 2 * LEN * i);       Q.x = F::to_mont(t);
+    load_be<N>(t.v, pts + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
+    return Q;
+  }
+  static EB_HD void store_point(uint8_t* out, size_t i, const aff& a) {
+    const size_t LEN = 4 * N;
+    fe x = F::from_mont(a.x), y = F::from_mont(a.y);
+    store_be<N>(out + 2 * LEN * i, x.v);
+    store_be<N>(out + 2 * LEN * i + LEN, y.v);
+  }
+
+  // ---- main: one signature
+  static EB_HD uint8_t verify_item(size_t i, size_t cnt_items, const uint8_t* pub, const uint8_t* r,
+                                   const u32* ws, const u32* gtab, u32* qtab) {
+    const size_t LEN = 4 * N;
+    u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
+    if (flags & FL_INVALID) return 0;   // ST_FALSE
+    aff Q = load_point(pub, i);
+    if (!on_curve(Q)) return 4;          // ST_NEEDS_HOST (un-validated off-curve key, SURVEY 8a Q1)
+    jac acc = dsm(i, cnt_items, Q, flags, ws, gtab, qtab);
     // accept iff R != O and x(R) == r (mod n)  (ec/index.js:222-228, eqXToP short.js:908-925)
     if (F::is_zero(acc.z)) return 0;
     fe z2 = F::sqr(acc.z);
@@ -271,6 +309,51 @@ struct SW {
       if (F::eq(acc.x, F::mul(F::to_mont(rn), z2))) return 1;
     }
     return 0;
+  }
+
+  // BasePoint.mul / Point.mulAdd (short.js:422-441) for an on-curve point, affine result (JPoint.toP,
+  // short.js:516-526).  1 = point written, 7 = infinity, 4 = off-curve (replayed by SWReplay).
+  static EB_HD uint8_t mul_add_item(size_t i, size_t cnt_items, const uint8_t* pts, const u32* ws, const u32* gtab,
+                                    u32* qtab, uint8_t* out) {
+    const size_t LEN = 4 * N;
+    for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
+    aff P = load_point(pts, i);
+    if (!on_curve(P)) return 4;
+    u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
+    jac acc = dsm(i, cnt_items, P, flags, ws, gtab, qtab);
+    if (F::is_zero(acc.z)) return 7;
+    store_point(out, i, to_aff(acc));
+    return 1;
+  }
+
+  // G.mul(k) (short.js:422-427 -> _fixedNafMul, base.js:52-84): fixed table only
+  static EB_HD uint8_t mul_g_item(size_t i, const uint8_t* k, const u32* gtab, uint8_t* out) {
+    const size_t LEN = 4 * N;
+    u32 nmod[N], kv[N];
+    n_limbs(nmod);
+    load_be<N>(kv, k + LEN * i);
+    if (geq_n<N>(kv, nmod)) sub_n<N>(kv, kv, nmod);
+    for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
+    if (is_zero_n<N>(kv)) return 7;
+    bool negg = (kv[0] & 1) == 0;
+    if (negg) sub_n<N>(kv, nmod, kv);
+    u32 m[N];
+    for (int w = 0; w < N; w++) m[w] = (kv[w] >> 1) | ((w < N - 1 ? kv[w + 1] : 0u) << 31);
+    jac acc = infinity();
+    for (int j = 0; j < GWINDOWS; j++) {
+      u32 chunk = extract(m, 1, 0, 0, GW * j, GW);
+      const u32 half = 1u << (GW - 1);
+      bool dneg = (j != GWINDOWS - 1) && (chunk < half);
+      u32 idx = (j == GWINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
+      const u32* ent = gtab + ((size_t)j * GENTRIES + idx) * 2 * N;
+      aff P;
+      P.x = load_fe_n<N>(ent);
+      P.y = load_fe_n<N>(ent + N);
+      P.y = F::cmov(P.y, F::neg(P.y), dneg != negg);
+      acc = madd(acc, P);
+    }
+    store_point(out, i, to_aff(acc));
+    return 1;
   }
 };
 

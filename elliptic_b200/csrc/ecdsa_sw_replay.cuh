@@ -25,32 +25,31 @@ struct SWReplay {
   static constexpr int TAB_WORDS = NAF_PTS * 2 * N;
   static constexpr int MAXLEN = 32 * N + 2;
 
-  static EB_HD void shr1(u32* a) {
-    for (int i = 0; i < N - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
-    a[N - 1] >>= 1;
-  }
-  static EB_HD int bitlen(const u32* a) {
-    for (int i = N - 1; i >= 0; i--)
-      if (a[i]) { int b = 32; while (!((a[i] >> (b - 1)) & 1)) b--; return 32 * i + b; }
-    return 0;
-  }
-  // utils.getNAF, utils.js:15-44
+  // utils.getNAF, utils.js:15-44.  One spare limb: k - z can exceed 2^(32N) for a raw scalar near the top.
   static EB_HD int get_naf(int16_t* naf, const u32* k, int w, int bits) {
-    int len = bitlen(k); if (bits > len) len = bits; len += 1;
+    constexpr int M = N + 1;
+    u32 t[M];
+    for (int q = 0; q < N; q++) t[q] = k[q];
+    t[N] = 0;
+    int len = 0;
+    for (int q = N - 1; q >= 0; q--)
+      if (k[q]) { int b = 32; while (!((k[q] >> (b - 1)) & 1)) b--; len = 32 * q + b; break; }
+    if (bits > len) len = bits;
+    len += 1;
     int ws = 1 << (w + 1);
-    u32 t[N]; copy_n<N>(t, k);
     for (int i = 0; i < len; i++) {
       int z = 0;
       int mod = (int)(t[0] & (u32)(ws - 1));
       if (t[0] & 1) {
         z = (mod > (ws >> 1) - 1) ? (ws >> 1) - mod : mod;
-        u32 zz[N];
-        for (int q = 0; q < N; q++) zz[q] = 0;
+        u32 zz[M];
+        for (int q = 0; q < M; q++) zz[q] = 0;
         zz[0] = (u32)(z < 0 ? -z : z);
-        if (z >= 0) sub_n<N>(t, t, zz); else add_n<N>(t, t, zz);
+        if (z >= 0) sub_n<M>(t, t, zz); else add_n<M>(t, t, zz);
       }
       naf[i] = (int16_t)z;
-      shr1(t);
+      for (int q = 0; q < M - 1; q++) t[q] = (t[q] >> 1) | (t[q + 1] << 31);
+      t[M - 1] >>= 1;
     }
     return len;
   }
@@ -102,6 +101,82 @@ struct SWReplay {
       }
     }
     return acc;
+  }
+
+  // ---- affine Point.add / Point.dbl with the reference's early-outs (short.js:365-412) ----------------
+  struct raff { fe x, y; bool inf; };
+  static EB_HD raff r_inf() { raff r; r.x = F::zero(); r.y = F::zero(); r.inf = true; return r; }
+  static EB_HD raff r_neg(const raff& p) { raff r = p; if (!p.inf) r.y = F::neg(p.y); return r; }
+  static EB_HD bool r_eq(const raff& a, const raff& b) {
+    return a.inf == b.inf && (a.inf || (F::eq(a.x, b.x) && F::eq(a.y, b.y)));
+  }
+  static EB_HD raff r_dbl(const raff& p) {
+    if (p.inf) return p;
+    fe ys1 = F::add(p.y, p.y);
+    if (F::is_zero(ys1)) return r_inf();
+    fe x2 = F::sqr(p.x);
+    fe dyinv = F::inv(ys1);
+    fe c = F::mul(F::sub(F::add(F::add(x2, x2), x2), C::three()), dyinv);      // (3x^2 + a) / 2y, a = -3
+    raff r; r.inf = false;
+    r.x = F::sub(F::sqr(c), F::add(p.x, p.x));
+    r.y = F::sub(F::mul(c, F::sub(p.x, r.x)), p.y);
+    return r;
+  }
+  static EB_HD raff r_add(const raff& a, const raff& b) {
+    if (a.inf) return b;
+    if (b.inf) return a;
+    if (r_eq(a, b)) return r_dbl(a);
+    if (r_eq(r_neg(a), b)) return r_inf();
+    if (F::eq(a.x, b.x)) return r_inf();
+    fe c = F::sub(a.y, b.y);
+    if (!F::is_zero(c)) c = F::mul(c, F::inv(F::sub(a.x, b.x)));
+    raff r; r.inf = false;
+    r.x = F::sub(F::sub(F::sqr(c), a.x), b.x);
+    r.y = F::sub(F::mul(c, F::sub(a.x, r.x)), a.y);
+    return r;
+  }
+
+  // BaseCurve._wnafMul(P, k) (base.js:86-126): w = 4 table P, 3P, .. by affine adds (_getNAFPoints,
+  // base.js:357-370; only the first 8 of its 15 entries can be indexed by a w = 4 NAF), Jacobian
+  // accumulator, runs of doublings, mixedAdd of +-table entries.
+  static EB_HD jac wnaf_mul(const u32* k, const aff& P) {
+    raff tab[8];
+    tab[0].x = P.x; tab[0].y = P.y; tab[0].inf = false;
+    raff d = r_dbl(tab[0]);
+    for (int t = 1; t < 8; t++) tab[t] = r_add(tab[t - 1], d);
+    int16_t naf[MAXLEN];
+    int len = get_naf(naf, k, 4, C::BITS);
+    jac acc = W::infinity();
+    for (int i = len - 1; i >= 0; i--) {
+      int l = 0;
+      for (; i >= 0 && naf[i] == 0; i--) l++;
+      if (i >= 0) l++;
+      if (!F::is_zero(acc.z))
+        for (int t = 0; t < l; t++) acc = W::dbl(acc);
+      if (i < 0) break;
+      int z = naf[i];
+      raff p = tab[((z < 0 ? -z : z) - 1) >> 1];
+      if (z < 0) p = r_neg(p);
+      if (p.inf) continue;                                   // mixedAdd: p.isInfinity() -> this
+      aff q; q.x = p.x; q.y = p.y;
+      acc = W::madd(acc, q);
+    }
+    return acc;
+  }
+
+  // Point.mul (k1 == nullptr) / G.mulAdd(k1, P, k2) for an off-curve P: the reference's schedule, then toP.
+  static EB_HD uint8_t mul_add_item(size_t i, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, const u32* tab,
+                                    uint8_t* out) {
+    const size_t LEN = 4 * N;
+    u32 u1[N], u2[N];
+    if (k1) load_be<N>(u1, k1 + LEN * i);
+    load_be<N>(u2, k2 + LEN * i);
+    aff P = W::load_point(pts, i);
+    jac acc = k1 ? jmul_add(u1, u2, P, tab) : wnaf_mul(u2, P);
+    for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
+    if (F::is_zero(acc.z)) return 7;
+    W::store_point(out, i, W::to_aff(acc));
+    return 1;
   }
 
   static EB_HD uint8_t verify_item(size_t i, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,

@@ -331,31 +331,33 @@ class EC:
 
     # ---- curve.point(...).mul / mulAdd batches (short.js:422-441) ---------------------------------------------
     def _scalars(self, ks):
-        out = np.zeros((len(ks), 32), np.uint8)
+        ln = self._len
+        out = np.zeros((len(ks), ln), np.uint8)
         for i, k in enumerate(ks):
             k = _bn(k)
             if k < 0:
                 raise EllipticError("negative scalars are not supported by the batch path")
-            if k >> 256:
+            if k >> (8 * ln):
                 k %= self.n          # same point for every on-curve input
-            out[i] = np.frombuffer(k.to_bytes(32, "big"), np.uint8)
+            out[i] = np.frombuffer(k.to_bytes(ln, "big"), np.uint8)
         return out
 
     def _points(self, pts):
         """curve.point(x, y) (short.js:251-271): coordinates reduced mod p, not validated."""
-        out = np.zeros((len(pts), 64), np.uint8)
+        ln = self._len
+        out = np.zeros((len(pts), 2 * ln), np.uint8)
         for i, pt in enumerate(pts):
             x, y = (pt["x"], pt["y"]) if isinstance(pt, dict) else pt
-            out[i, :32] = np.frombuffer((_bn(x) % self._c["p"]).to_bytes(32, "big"), np.uint8)
-            out[i, 32:] = np.frombuffer((_bn(y) % self._c["p"]).to_bytes(32, "big"), np.uint8)
+            out[i, :ln] = np.frombuffer((_bn(x) % self._c["p"]).to_bytes(ln, "big"), np.uint8)
+            out[i, ln:] = np.frombuffer((_bn(y) % self._c["p"]).to_bytes(ln, "big"), np.uint8)
         return out
 
     def _mul_common(self, k1, k2, pts):
-        if self.name != "secp256k1":
-            raise EllipticError("mul/mulAdd batches: only secp256k1 is accelerated")
+        if self.name not in ("secp256k1", "p256", "p384"):
+            raise EllipticError("mul/mulAdd batches: short curves only")
         lib = nat.init(self._device)
-        n = len(k2)
-        out = np.zeros((n, 64), np.uint8)
+        n, ln = len(k2), self._len
+        out = np.zeros((n, 2 * ln), np.uint8)
         st = np.zeros(n, np.uint8)
         if k1 is None:
             nat.check(lib.eb200_scalar_mul_batch(self._c["id"], n, k2.ctypes.data, pts.ctypes.data if pts is not None else None,
@@ -363,7 +365,7 @@ class EC:
         else:
             nat.check(lib.eb200_mul_add_batch(self._c["id"], n, k1.ctypes.data, k2.ctypes.data, pts.ctypes.data,
                                               out.ctypes.data, st.ctypes.data))
-        return [(int.from_bytes(out[i, :32].tobytes(), "big"), int.from_bytes(out[i, 32:].tobytes(), "big"))
+        return [(int.from_bytes(out[i, :ln].tobytes(), "big"), int.from_bytes(out[i, ln:].tobytes(), "big"))
                 if st[i] == nat.ST_TRUE else None for i in range(n)]
 
     def g_mul_batch(self, ks):

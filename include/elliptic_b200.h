@@ -111,17 +111,18 @@ int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t*
 int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s,
                               const uint8_t* recid, uint8_t* out_xy, uint8_t* status);
 
-/* Batch of BasePoint.mul (lib/elliptic/curve/short.js:422-432), secp256k1:
- *   k         : n x 32 big-endian scalars, any value below 2^256 (the reference does not reduce them)
- *   points_xy : n x 64 x || y big-endian, or NULL for the base point (G.mul(k) -> _fixedNafMul, base.js:52-84)
- *   out_xy    : n x 64 affine result as Point.toP / getX / getY give it (zeroed unless status is TRUE)
+/* Batch of BasePoint.mul (lib/elliptic/curve/short.js:422-432) on secp256k1 / p256 / p384 (len = 32/32/48):
+ *   k         : n x len big-endian scalars, any value below 2^(8 len) (the reference does not reduce them)
+ *   points_xy : n x 2len x || y big-endian, or NULL for the base point (G.mul(k) -> _fixedNafMul, base.js:52-84)
+ *   out_xy    : n x 2len affine result as Point.toP / getX / getY give it (zeroed unless status is TRUE)
  * status: TRUE (point written) or INFINITY.  Points are not validated, exactly as `curve.point(x, y)`
  * (short.js:251-271); an off-curve point gets the result of the reference's own add/double sequence. */
 int eb200_scalar_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* points_xy, uint8_t* out_xy,
                            uint8_t* status);
 
-/* Batch of G.mulAdd(k1, P2, k2) = k1*G + k2*P2 (lib/elliptic/curve/short.js:434-441, _endoWnafMulAdd
- * short.js:218-249), secp256k1.  Arguments and status as eb200_scalar_mul_batch. */
+/* Batch of G.mulAdd(k1, P2, k2) = k1*G + k2*P2 (lib/elliptic/curve/short.js:434-441; _endoWnafMulAdd
+ * short.js:218-249 on secp256k1, _wnafMulAdd base.js:128-253 on p256 / p384).  Arguments and status as
+ * eb200_scalar_mul_batch. */
 int eb200_mul_add_batch(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* p2_xy,
                         uint8_t* out_xy, uint8_t* status);
 

@@ -245,3 +245,30 @@ extern "C" void he_mul_add(size_t N, const uint8_t* k1, const uint8_t* k2, const
 extern "C" void he_mul_g(size_t N, const uint8_t* k, const u32* gtab, uint8_t* out, uint8_t* status) {
   for (size_t i = 0; i < N; i++) status[i] = k256_mul_g_item(i, k, gtab, out);
 }
+
+// Point.mul / mulAdd on p256 / p384: fast path + exact replay
+template <class C>
+static void sw_mul_add_host(size_t N, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, uint8_t* out, uint8_t* status) {
+  typedef SW<C> W;
+  // reuse the verify helper's table by running it once on zero items
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)W::GWINDOWS * W::GENTRIES * 2 * W::N);
+    for (int j = 0; j < W::GWINDOWS; j++)
+      for (int i = 0; i < W::GENTRIES; i++) W::gtab_entry(j, i, &gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N]);
+  }
+  if (!pts) {
+    for (size_t i = 0; i < N; i++) status[i] = W::mul_g_item(i, k2, gtab.data(), out);
+    return;
+  }
+  std::vector<u32> ws((size_t)W::PREP_WORDS * N), qtab((size_t)W::QTAB_WORDS * N);
+  for (size_t i = 0; i < N; i++) W::prep_scalars_item(i, N, k1, k2, ws.data());
+  for (size_t i = 0; i < N; i++) {
+    status[i] = W::mul_add_item(i, N, pts, ws.data(), gtab.data(), qtab.data(), out);
+    if (status[i] == 4) status[i] = SWReplay<C>::mul_add_item(i, k1, k2, pts, sw_replay_tab<C>().data(), out);
+  }
+}
+extern "C" void he_sw_mul_add(int curve, size_t N, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, uint8_t* out, uint8_t* status) {
+  if (curve == 2) sw_mul_add_host<P256>(N, k1, k2, pts, out, status);
+  else sw_mul_add_host<P384>(N, k1, k2, pts, out, status);
+}

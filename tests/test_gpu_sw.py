@@ -178,3 +178,29 @@ def test_sec1_key_formats_on_gpu(native, name):
     assert [int(v) for v in st_c] == exp_c
     assert [int(v) for v in st_u] == exp_u
     assert {1, 0, 2, 6} <= set(exp_c) and {1, 5, 6} <= set(exp_u)
+
+
+@pytest.mark.parametrize("name", ["p256", "p384"])
+def test_mul_and_mul_add_batches(native, name):
+    """curve.point(x, y).mul(k) (_wnafMul), G.mul(k), G.mulAdd(k1, P, k2) (short.js:422-441) on the non-GLV
+    curves: hostemu edge cases (oversize / zero scalars, P = +-G, off-curve points) plus random items."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_hostemu_k256 import mul_cases
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    cid, ln = CURVES[name]
+    ec = EC(name)
+    rnd = random.Random(13)
+    cases = mul_cases(ec, seed=7, bits=8 * ln)
+    base = [ec.g.mul(rnd.randrange(1, ec.n)) for _ in range(4)]
+    for t in range(60):
+        P = base[t % 4]
+        cases.append((rnd.randrange(2 ** (8 * ln)), rnd.randrange(2 ** (8 * ln)), P.x, P.y))
+    ref = lambda pt: None if pt.is_infinity() else (pt.get_x(), pt.get_y())
+    g = GpuEC(name)
+    pts = [(c[2], c[3]) for c in cases]
+    assert g.mul_add_batch([c[0] for c in cases], pts, [c[1] for c in cases]) == \
+        [ref(ec.g.mul_add(c[0], ec.curve.point(c[2], c[3]), c[1])) for c in cases]
+    assert g.mul_batch(pts, [c[1] for c in cases]) == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
+    assert g.g_mul_batch([c[1] for c in cases]) == [ref(ec.g.mul(c[1])) for c in cases]

@@ -228,7 +228,7 @@ def test_sw_replay_verdicts_for_off_curve_keys(he, name, cid, ln):
     assert 1 in exp and 0 in exp
 
 
-def mul_cases(ec, seed=3):
+def mul_cases(ec, seed=3, bits=256):
     """(k1, k2, x, y) for Point.mul / mulAdd: ordinary, oversize, zero and cancelling scalars, P = +-G,
     off-curve points (short.js:251-271 never validates)."""
     rnd = random.Random(seed)
@@ -241,14 +241,39 @@ def mul_cases(ec, seed=3):
     Pd = G.mul(d)
     cases += [
         (0, 5, P1.x, P1.y), (7, 0, P1.x, P1.y), (0, 0, P1.x, P1.y),
-        (n + 3, 2**256 - 1, P1.x, P1.y),                       # not reduced by the reference
+        (n + 3 if n + 3 < 2**bits else 3, 2**bits - 1, P1.x, P1.y),                       # not reduced by the reference
         ((n - d * 9 % n) % n, 9, Pd.x, Pd.y),                  # k1*G + k2*P = O
         (5, 1, G.x, G.y), (5, n - 5, G.x, G.y), (1, 1, G.x, p - G.y),
         (rnd.randrange(n), rnd.randrange(n), rnd.randrange(p), rnd.randrange(p)),     # off-curve
         (rnd.randrange(n), rnd.randrange(n), 0, 0),
-        (3, 2**256 - 5, rnd.randrange(p), rnd.randrange(p)),
+        (3, 2**bits - 5, rnd.randrange(p), rnd.randrange(p)),
     ]
     return cases
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+def test_sw_mul_and_mul_add_bodies_against_oracle(he, name, cid, ln):
+    from oracle.ref_py.ec import EC
+    ec = EC(name)
+    cases = mul_cases(ec, seed=6, bits=8 * ln)
+    n = len(cases)
+    k1 = b"".join(c[0].to_bytes(ln, "big") for c in cases)
+    k2 = b"".join(c[1].to_bytes(ln, "big") for c in cases)
+    pts = b"".join(c[2].to_bytes(ln, "big") + c[3].to_bytes(ln, "big") for c in cases)
+
+    def unpack(out, st):
+        return [(int.from_bytes(bytes(out[2 * ln * i:2 * ln * i + ln]), "big"), int.from_bytes(bytes(out[2 * ln * i + ln:2 * ln * (i + 1)]), "big"))
+                if st[i] == 1 else None for i in range(n)]
+
+    ref = lambda pt: None if pt.is_infinity() else (pt.get_x(), pt.get_y())
+    out = (ctypes.c_uint8 * (2 * ln * n))(); st = (ctypes.c_uint8 * n)()
+    he.he_sw_mul_add(cid, ctypes.c_size_t(n), k1, k2, pts, out, st)
+    assert unpack(out, st) == [ref(ec.g.mul_add(c[0], ec.curve.point(c[2], c[3]), c[1])) for c in cases]
+    assert set(st) == {1, 7}
+    he.he_sw_mul_add(cid, ctypes.c_size_t(n), None, k2, pts, out, st)
+    assert unpack(out, st) == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
+    he.he_sw_mul_add(cid, ctypes.c_size_t(n), None, k2, None, out, st)
+    assert unpack(out, st) == [ref(ec.g.mul(c[1])) for c in cases]
 
 
 def test_mul_and_mul_add_bodies_against_oracle(he):
