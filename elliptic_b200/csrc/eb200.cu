@@ -10,6 +10,7 @@
 #include "ecdsa_k256_body.cuh"
 #include "ecdsa_k256_replay.cuh"
 #include "ecdsa_sw_replay.cuh"
+#include "ecdsa_k256_sign_fast.cuh"
 #include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
@@ -68,12 +69,28 @@ k256_recover_kernel(size_t N, const uint8_t* __restrict__ r, const uint8_t* __re
   status[i] = recover_item(i, N, r, recid, ws, gtab, qtab, out);
 }
 
+// Two-kernel signing pipeline (ecdsa_k256_sign_fast.cuh); k256_sign_slow_kernel redoes flagged items with
+// the literal retry loop of k256_sign_item.
 __global__ void __launch_bounds__(128)
-k256_sign_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
-                 const u32* __restrict__ gtab, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
-                 uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+k256_sign_nonce_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv,
+                       const u32* __restrict__ gtab, u32* __restrict__ ws, uint8_t* __restrict__ status) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+  if (i < N) k256_sign_nonce_item(i, N, e, priv, gtab, ws, status);
+}
+__global__ void __launch_bounds__(128)
+k256_sign_finish_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
+                        const u32* __restrict__ ws, u32* __restrict__ scratch, uint8_t* __restrict__ r,
+                        uint8_t* __restrict__ s, uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  k256_sign_finish_thread(tid, T, N, e, priv, canonical, ws, scratch, r, s, recid, status);
+}
+__global__ void __launch_bounds__(128)
+k256_sign_slow_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
+                      const u32* __restrict__ gtab, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
+                      uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
   status[i] = k256_sign_item(i, e, priv, canonical, gtab, r, s, recid);
 }
 
@@ -864,14 +881,23 @@ int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t*
   if (rc) return rc;
   if ((rc = grow(&g.d_in, &g.d_in_cap, n * (4 * 32 + 1) + 256))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  const size_t ws_bytes = align256((size_t)SIGN_WS_WORDS * 4 * n);
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_bytes + (size_t)SIGN_SCRATCH_WORDS * 4 * n))) return rc;
   uint8_t *d_e = g.d_in, *d_k = d_e + 32 * n, *d_r = d_k + 32 * n, *d_s = d_r + 32 * n, *d_id = d_s + 32 * n;
+  u32 *d_sws = (u32*)g.d_ws, *d_scr = (u32*)(g.d_ws + ws_bytes);
+  const u32 canonical = flags & EB200_SIGN_CANONICAL;
   cudaStream_t st = g.stream;
   CK(cudaEventRecord(g.ev[0], st));
   CK(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_k, priv, 32 * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
-  k256_sign_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, d_e, d_k, flags & EB200_SIGN_CANONICAL, g.gtab[curve],
-                                                              d_r, d_s, d_id, g.d_status);
+  unsigned nb = (unsigned)((n + 127) / 128);
+  size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
+  k256_sign_nonce_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, g.gtab[curve], d_sws, g.d_status);
+  CK(cudaGetLastError());
+  k256_sign_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, g.d_status);
+  CK(cudaGetLastError());
+  k256_sign_slow_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, canonical, g.gtab[curve], d_r, d_s, d_id, g.d_status);
   CK(cudaGetLastError());
   CK(cudaEventRecord(g.ev[2], st));
   CK(cudaMemcpyAsync(out_r, d_r, 32 * n, cudaMemcpyDeviceToHost, st));
@@ -886,7 +912,7 @@ int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t*
   cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
   cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
   g.timing.main_kernel_ms = g.timing.kernel_ms;
-  g.timing.launches = 1;
+  g.timing.launches = 3;
   return EB200_OK;
 }
 

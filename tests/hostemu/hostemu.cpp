@@ -272,3 +272,31 @@ extern "C" void he_sw_mul_add(int curve, size_t N, const uint8_t* k1, const uint
   if (curve == 2) sw_mul_add_host<P256>(N, k1, k2, pts, out, status);
   else sw_mul_add_host<P384>(N, k1, k2, pts, out, status);
 }
+
+// ---------------------------------------------------------------------------
+// two-kernel signing pipeline (nonce -> finish -> flagged items through the literal loop)
+#include "../../elliptic_b200/csrc/ecdsa_k256_sign_fast.cuh"
+extern "C" void he_sign_fast(size_t N, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,
+                             uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status, int force_slow_every) {
+  std::vector<u32> ws((size_t)SIGN_WS_WORDS * N), scratch((size_t)SIGN_SCRATCH_WORDS * N);
+  for (size_t i = 0; i < N; i++) k256_sign_nonce_item(i, N, e, priv, gtab, ws.data(), status);
+  if (force_slow_every)      // exercise the fallback: pretend the nonce kernel flagged every k-th item
+    for (size_t i = 0; i < N; i += force_slow_every) {
+      status[i] = ST_NEEDS_HOST;
+      for (int w = 0; w < 8; w++) { ws[(size_t)(16 + w) * N + i] = w == 0; ws[(size_t)(24 + w) * N + i] = w == 0; }
+    }
+  size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
+  for (size_t t = 0; t < T; t++)
+    k256_sign_finish_thread(t, T, N, e, priv, canonical, ws.data(), scratch.data(), r, s, recid, status);
+  for (size_t i = 0; i < N; i++)
+    if (status[i] == ST_NEEDS_HOST) status[i] = k256_sign_item(i, e, priv, canonical, gtab, r, s, recid);
+}
+extern "C" void he_drbg_first_k(const uint8_t* priv, const uint8_t* msg, uint8_t* out) {
+  u32 d[8], m[8], k[8];
+  for (int w = 0; w < 8; w++) {
+    d[w] = ((u32)priv[4 * w] << 24) | ((u32)priv[4 * w + 1] << 16) | ((u32)priv[4 * w + 2] << 8) | priv[4 * w + 3];
+    m[w] = ((u32)msg[4 * w] << 24) | ((u32)msg[4 * w + 1] << 16) | ((u32)msg[4 * w + 2] << 8) | msg[4 * w + 3];
+  }
+  drbg_first_k(d, m, k);
+  for (int w = 0; w < 8; w++) for (int b = 0; b < 4; b++) out[4 * w + b] = (uint8_t)(k[w] >> (24 - 8 * b));
+}

@@ -163,6 +163,20 @@ def test_sign_and_hash_bodies_against_oracle(he):
             sig = ec.sign(ev.to_bytes(32, "big"), dv, canonical=bool(canon))
             assert (int.from_bytes(bytes(r[32 * i:32 * i + 32]), "big"), int.from_bytes(bytes(s[32 * i:32 * i + 32]), "big"),
                     rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1)
+    # the two-kernel pipeline (word-oriented DRBG, batched inversions) must give the same bytes, with and
+    # without items routed through the literal retry loop
+    items = items + [(rnd.randrange(ec.n), rnd.randrange(1, ec.n)) for _ in range(25)]
+    n = len(items)
+    e = b"".join(x.to_bytes(32, "big") for x, _ in items)
+    d = b"".join(y.to_bytes(32, "big") for _, y in items)
+    for canon, every in ((0, 0), (1, 0), (1, 5)):
+        r, s = (ctypes.c_uint8 * (32 * n))(), (ctypes.c_uint8 * (32 * n))()
+        rec, st = (ctypes.c_uint8 * n)(), (ctypes.c_uint8 * n)()
+        he.he_sign_fast(ctypes.c_size_t(n), e, d, canon, gtab.ctypes.data_as(ctypes.c_void_p), r, s, rec, st, every)
+        for i, (ev, dv) in enumerate(items):
+            sig = ec.sign(ev.to_bytes(32, "big"), dv, canonical=bool(canon))
+            assert (int.from_bytes(bytes(r[32 * i:32 * i + 32]), "big"), int.from_bytes(bytes(s[32 * i:32 * i + 32]), "big"),
+                    rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1), (i, canon, every)
     ed = EDDSA()
     eit = ed_items(limit=16)
     m = len(eit)
