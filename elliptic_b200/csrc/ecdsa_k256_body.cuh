@@ -52,14 +52,6 @@ static_assert(255 - GTAB_W * (GTAB_WINDOWS - 1) <= GTAB_W - 1, "top digit 2m+1 m
 
 struct madd_out { ge_jac r; fe h; };
 
-EB_HD void eb_prefetch(const void* p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 #if defined(__CUDACC__)
 #define EB_FN __host__ __device__ __noinline__
 #else
@@ -282,35 +274,21 @@ EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32*
     }
   }
 
-  // ---- u2*Q = k1*Q + k2*(lambda*Q): 33 windows of 4 bits, regular signed-odd digits.
-  // Software-pipelined by one window: the digit words of the next window are loaded, and this window's
-  // two table entries are prefetched into L1, before the four doublings that precede their use
-  // (ncu r01: first use of a loaded entry was the kernel's top long-scoreboard stall).
+  // ---- u2*Q = k1*Q + k2*(lambda*Q): 33 windows of 4 bits, regular signed-odd digits
   ge_jac acc = jac_infinity();
-  u32 cw0 = ws[(size_t)(8 + 4) * N + i], cw1 = ws[(size_t)(13 + 4) * N + i];
   for (int w = 32; w >= 0; w--) {
-    u32 idx[2]; bool neg[2];
-    for (int h = 0; h < 2; h++) {
-      u32 nib = ((h ? cw1 : cw0) >> (4 * (w & 7))) & 15;
-      bool dneg = (w != 32) && (nib < 8);
-      idx[h] = (w == 32) ? (nib & 7) : (dneg ? 7 - nib : nib - 8);
-      neg[h] = dneg != (((flags & (h ? FL_NEG2 : FL_NEG1)) != 0));
-    }
-    eb_prefetch(tab + 24 * idx[0]);
-    eb_prefetch(tab + 24 * idx[0] + 8);
-    eb_prefetch(tab + 24 * idx[1] + 8);
-    eb_prefetch(tab + 24 * idx[1] + 16);
-    if (w > 0 && ((w - 1) & 7) == 7) {
-      cw0 = ws[(size_t)(8 + ((w - 1) >> 3)) * N + i];
-      cw1 = ws[(size_t)(13 + ((w - 1) >> 3)) * N + i];
-    }
     if (w != 32)
       for (int d = 0; d < 4; d++) acc = jac_dbl(acc);   // (the top window starts from its first table entry)
     for (int h = 0; h < 2; h++) {
+      u32 word = ws[(size_t)((h ? 13 : 8) + (w >> 3)) * N + i];
+      u32 nib = (word >> (4 * (w & 7))) & 15;
+      bool dneg = (w != 32) && (nib < 8);
+      u32 idx = (w == 32) ? (nib & 7) : (dneg ? 7 - nib : nib - 8);
+      bool neg = dneg != (((flags & (h ? FL_NEG2 : FL_NEG1)) != 0));
       ge_aff P;
-      P.x = load_fe(tab + 24 * idx[h] + (h ? 16 : 0));
-      P.y = load_fe(tab + 24 * idx[h] + 8);
-      P = aff_neg_if(P, neg[h]);
+      P.x = load_fe(tab + 24 * idx + (h ? 16 : 0));
+      P.y = load_fe(tab + 24 * idx + 8);
+      P = aff_neg_if(P, neg);
       if (w == 32 && h == 0) acc = jac_from_aff(P);
       else acc = jac_madd(acc, P);
     }
@@ -318,30 +296,19 @@ EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32*
   // back to the real curve: Z *= Zg
   acc.z = fe_mul(acc.z, zglobal);
 
-  // ---- u1*G from the fixed table: GTAB_WINDOWS windows of GTAB_W bits, regular signed-odd digits;
-  // entry j+1 is prefetched while the mixed add of entry j runs
+  // ---- u1*G from the fixed table: GTAB_WINDOWS windows of GTAB_W bits, regular signed-odd digits
   if (flags & FL_NOG) return acc;             // Point.mul: no base-point term (uniform across a batch)
-  const u32* ent_next = nullptr;
-  bool neg_next = false;
-  for (int j = -1; j < GTAB_WINDOWS; j++) {
-    const u32* ent = ent_next;
-    bool neg = neg_next;
-    if (j + 1 < GTAB_WINDOWS) {
-      const int jn = j + 1;
-      const int pos = GTAB_W * jn;
-      u32 lo = ws[(size_t)(pos >> 5) * N + i];
-      u32 hi = ((pos >> 5) < 7) ? ws[(size_t)((pos >> 5) + 1) * N + i] : 0u;
-      u64 both = ((u64)hi << 32) | lo;
-      u32 chunk = (u32)(both >> (pos & 31)) & ((1u << GTAB_W) - 1);
-      const u32 half = 1u << (GTAB_W - 1);
-      bool dneg = (jn != GTAB_WINDOWS - 1) && (chunk < half);
-      u32 idxg = (jn == GTAB_WINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
-      neg_next = dneg != ((flags & FL_NEGG) != 0);
-      ent_next = gtab + ((size_t)jn * GTAB_ENTRIES + idxg) * 16;
-      eb_prefetch(ent_next);
-      eb_prefetch(ent_next + 8);
-    }
-    if (j < 0) continue;
+  for (int j = 0; j < GTAB_WINDOWS; j++) {
+    const int pos = GTAB_W * j;
+    u32 lo = ws[(size_t)(pos >> 5) * N + i];
+    u32 hi = ((pos >> 5) < 7) ? ws[(size_t)((pos >> 5) + 1) * N + i] : 0u;
+    u64 both = ((u64)hi << 32) | lo;
+    u32 chunk = (u32)(both >> (pos & 31)) & ((1u << GTAB_W) - 1);
+    const u32 half = 1u << (GTAB_W - 1);
+    bool dneg = (j != GTAB_WINDOWS - 1) && (chunk < half);
+    u32 idx = (j == GTAB_WINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
+    bool neg = dneg != ((flags & FL_NEGG) != 0);
+    const u32* ent = gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16;
     ge_aff P;
     P.x = load_fe(ent);
     P.y = load_fe(ent + 8);
