@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <cstdlib>
 #include <mutex>
 #include "../../include/elliptic_b200.h"
 #include "ecdsa_k256_body.cuh"
@@ -374,7 +375,7 @@ constexpr int MAX_CHUNKS = 16;
 struct Ctx {
   bool ready = false;
   int device = -1;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
   u32* gtab[8] = {};
   u32* sw_replay_tab[8] = {};         // p256/p384: the reference's wnd-8 NAF table of G
   u32* replay_tab = nullptr;          // secp256k1: the reference's wnd-7 NAF table of G and its beta image
@@ -568,6 +569,7 @@ int eb200_init(int device) {
   CK(cudaSetDevice(device));
   if (!g.stream) CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   if (!g.copy_stream) CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  if (!g.stream2) CK(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
   for (int i = 0; i < 6; i++) if (!g.ev[i]) CK(cudaEventCreate(&g.ev[i]));
   for (int i = 0; i < MAX_CHUNKS; i++) {
     if (!g.ev_in[i]) CK(cudaEventCreate(&g.ev_in[i]));
@@ -605,6 +607,7 @@ int eb200_shutdown(void) {
   }
   if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
   if (g.copy_stream) { cudaStreamDestroy(g.copy_stream); g.copy_stream = nullptr; }
+  if (g.stream2) { cudaStreamDestroy(g.stream2); g.stream2 = nullptr; }
   g.ready = false;
   return EB200_OK;
 }
@@ -666,17 +669,20 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   int chunks = 1;
   if (n >= ((size_t)1 << 18)) chunks = 4;     // 2^18-item chunks keep the grid tail small (r01: 8 chunks cost 10%)
   if (n >= ((size_t)1 << 22)) chunks = MAX_CHUNKS;
+  if (const char* ev = getenv("EB200_CHUNKS")) { int c = atoi(ev); if (c >= 1 && c <= MAX_CHUNKS) chunks = c; }   // tuning knob
   size_t per = (n + chunks - 1) / chunks;
   per = (per + 127) & ~(size_t)127;
   size_t item_in = 3 * len + pb;
   if ((rc = grow(&g.d_in, &g.d_in_cap, align256(n * item_in) + 1024))) return rc;
-  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_layout(curve, per).total))) return rc;
+  // two chunks in flight (alternating compute streams, so the grid tail of chunk k is filled by chunk k+1)
+  const size_t ws_slot = ws_layout(curve, per).total;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, (chunks > 1 ? 2 : 1) * ws_slot))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
   uint8_t* d_e = g.d_in;
   uint8_t* d_r = d_e + n * len;
   uint8_t* d_s = d_r + n * len;
   uint8_t* d_pub = d_s + n * len;
-  cudaStream_t cs = g.copy_stream, ks = g.stream;
+  cudaStream_t cs = g.copy_stream;
   unsigned launches = 0;
   CK(cudaEventRecord(g.ev[0], cs));
   int used = 0;
@@ -690,9 +696,10 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
     CK(cudaMemcpyAsync(d_s + lo * len, s + lo * len, m * len, cudaMemcpyHostToDevice, cs));
     CK(cudaMemcpyAsync(d_pub + lo * pb, pub + lo * pb, m * pb, cudaMemcpyHostToDevice, cs));
     CK(cudaEventRecord(g.ev_in[k], cs));
+    cudaStream_t ks = (k & 1) ? g.stream2 : g.stream;
     CK(cudaStreamWaitEvent(ks, g.ev_in[k], 0));
     if ((rc = launch_verify(curve, m, d_e + lo * len, d_r + lo * len, d_s + lo * len, d_pub + lo * pb, pub_fmt,
-                            g.d_status + lo, g.d_ws, ks, g.ev_k0[k], g.ev_k1[k], &launches))) return rc;
+                            g.d_status + lo, g.d_ws + (size_t)(k & 1) * ws_slot, ks, g.ev_k0[k], g.ev_k1[k], &launches))) return rc;
     CK(cudaEventRecord(g.ev_done[k], ks));
   }
   // results: one device->host copy per chunk, behind that chunk's kernels, on the copy stream
@@ -704,7 +711,8 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   }
   CK(cudaEventRecord(g.ev[3], cs));
   CK(cudaStreamSynchronize(cs));
-  CK(cudaStreamSynchronize(ks));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaStreamSynchronize(g.stream2));
   g.dev_timing_pending = false;
   g.timing = eb200_timing{};
   float total = 0, t = 0;
