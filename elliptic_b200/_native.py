@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("EB200_LIB") or os.path.join(_HERE, "libelliptic_b200.
 OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_NOT_INIT, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 ST_FALSE, ST_TRUE, ST_THROW_INVALID_POINT, ST_THROW_NOT_VALIDATED, ST_NEEDS_HOST, ST_THROW_ASSERT, \
     ST_THROW_POINT_FORMAT = range(7)
-ST_INFINITY, ST_THROW_SECOND_KEY = 7, 8
+ST_INFINITY, ST_THROW_SECOND_KEY, ST_THROW_SIG_FORMAT = 7, 8, 9
 CURVE_SECP256K1, CURVE_P256, CURVE_P384, CURVE_ED25519, CURVE_CURVE25519 = 1, 2, 3, 4, 5
 PUB_XY, PUB_SEC1_65, PUB_SEC1_33 = 0, 1, 2
 
@@ -24,6 +24,7 @@ EXPORTS = [
     "eb200_eddsa_verify_batch", "eb200_eddsa_verify_workspace_bytes", "eb200_eddsa_verify_batch_dev",
     "eb200_x25519_derive_batch", "eb200_x25519_derive_batch_dev", "eb200_ecdsa_recover_batch", "eb200_ecdsa_sign_batch",
     "eb200_eddsa_verify_batch_msgs", "eb200_scalar_mul_batch", "eb200_mul_add_batch",
+    "eb200_ecdsa_verify_batch_der",
 ]
 
 
@@ -68,6 +69,7 @@ def load():
     lib.eb200_eddsa_verify_batch_msgs.argtypes = [c.c_size_t] + [c.c_void_p] * 6
     lib.eb200_ecdsa_sign_batch.argtypes = [c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_uint32] + [c.c_void_p] * 4
     lib.eb200_ecdsa_recover_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 6
+    lib.eb200_ecdsa_verify_batch_der.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4 + [c.c_uint32, c.c_void_p]
     lib.eb200_scalar_mul_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4
     lib.eb200_mul_add_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 5
     lib.eb200_selftest_gtab_dims.argtypes = [c.c_int] + [c.c_void_p] * 3

@@ -12,6 +12,7 @@
 #include "ecdsa_k256_replay.cuh"
 #include "ecdsa_sw_replay.cuh"
 #include "ecdsa_k256_sign_fast.cuh"
+#include "der_sig.cuh"
 #include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
@@ -136,6 +137,20 @@ k256_mul_g_kernel(size_t N, const uint8_t* __restrict__ k, const u32* __restrict
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   status[i] = k256_mul_g_item(i, k, gtab, out);
+}
+
+// DER signatures -> fixed-width r, s (Signature._importDER, ec/signature.js:73-134).  `pre` carries the
+// key-decoding verdict when there is one: a key that throws wins, as keyFromPublic runs first
+// (ec/index.js:194-195).
+__global__ void __launch_bounds__(128)
+der_decode_kernel(size_t N, u32 len, const uint8_t* __restrict__ der, const unsigned long long* __restrict__ off,
+                  uint8_t* __restrict__ r, uint8_t* __restrict__ s, uint8_t* __restrict__ pre, int pre_valid) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  bool ok = der_import(der + off[i], (size_t)(off[i + 1] - off[i]), len, r + (size_t)len * i, s + (size_t)len * i);
+  uint8_t st = pre_valid ? pre[i] : 0;
+  if (!st && !ok) st = ST_THROW_SIG_FORMAT;
+  pre[i] = st;
 }
 
 // SEC1 decode (BaseCurve.decodePoint, lib/elliptic/curve/base.js:270-292; pointFromX short.js:187-204)
@@ -481,7 +496,8 @@ int ensure_table(int curve) {
 // Launches decode (if needed) + prep + verify for n items on stream st.  All pointers are device pointers.
 int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, const uint8_t* d_s,
                   const uint8_t* d_pub, u32 pub_fmt, uint8_t* d_status, uint8_t* d_workspace,
-                  cudaStream_t st, cudaEvent_t ev_main0, cudaEvent_t ev_main1, unsigned* launches) {
+                  cudaStream_t st, cudaEvent_t ev_main0, cudaEvent_t ev_main1, unsigned* launches,
+                  const uint8_t* d_der = nullptr, const unsigned long long* d_der_off = nullptr) {
   if (n == 0) return EB200_OK;
   WsLayout L = ws_layout(curve, n);
   u32* ws = (u32*)(d_workspace + L.ws);
@@ -501,6 +517,12 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     else sw_decode_pub_kernel<P384><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
     CK(cudaGetLastError());
     xy = dxy; pre = dpre; cnt++;
+  }
+  if (d_der) {     // d_r / d_s are then scratch the decoder fills
+    uint8_t* dpre = d_workspace + L.pre;
+    der_decode_kernel<<<nb, 128, 0, st>>>(n, (u32)curve_len(curve), d_der, d_der_off, (uint8_t*)d_r, (uint8_t*)d_s, dpre, pre != nullptr);
+    CK(cudaGetLastError());
+    pre = dpre; cnt++;
   }
   if (curve == EB200_CURVE_SECP256K1) {
     k256_prep_kernel<<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
@@ -725,6 +747,55 @@ int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_
   cudaEventElapsedTime(&t, g.ev_done[used - 1], g.ev[3]);
   g.timing.d2h_ms = t;                                                       // exposed tail copy
   g.timing.kernel_ms = total;                                                // whole call on the GPU timeline
+  g.timing.launches = launches;
+  return EB200_OK;
+}
+
+// DER-encoded signatures, parsed on the GPU (variable length: concatenated bytes + n+1 offsets)
+int eb200_ecdsa_verify_batch_der(int curve, size_t n, const uint8_t* e, const uint8_t* sigs, const uint64_t* sig_off,
+                                 const uint8_t* pub, uint32_t pub_fmt, uint8_t* status) {
+  if (!g.ready) return EB200_ERR_NOT_INIT;
+  if (!curve_ok(curve) || !fmt_ok(pub_fmt)) return EB200_ERR_UNSUPPORTED;
+  if (n == 0) return EB200_OK;
+  if (!e || !sigs || !sig_off || !pub || !status) return EB200_ERR_ARG;
+  for (size_t i = 0; i < n; i++) if (sig_off[i + 1] < sig_off[i]) return EB200_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_mu);
+  CK(cudaSetDevice(g.device));
+  int rc = ensure_table(curve);
+  if (rc) return rc;
+  const size_t len = curve_len(curve), pb = pub_item_bytes(len, pub_fmt);
+  const size_t sig_bytes = (size_t)(sig_off[n] - sig_off[0]);
+  const size_t off_bytes = align256((n + 1) * 8);
+  if ((rc = grow(&g.d_in, &g.d_in_cap, off_bytes + align256(n * (3 * len + pb)) + align256(sig_bytes) + 1024))) return rc;
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_layout(curve, n).total))) return rc;
+  if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
+  unsigned long long* d_off = (unsigned long long*)g.d_in;
+  uint8_t* d_e = g.d_in + off_bytes;
+  uint8_t* d_r = d_e + n * len;
+  uint8_t* d_s = d_r + n * len;
+  uint8_t* d_pub = d_s + n * len;
+  uint8_t* d_sig = d_pub + align256(n * pb);
+  cudaStream_t st = g.stream;
+  unsigned launches = 0;
+  CK(cudaEventRecord(g.ev[0], st));
+  CK(cudaMemcpyAsync(d_off, sig_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_e, e, n * len, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_pub, pub, n * pb, cudaMemcpyHostToDevice, st));
+  if (sig_bytes) CK(cudaMemcpyAsync(d_sig, sigs + sig_off[0], sig_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(g.ev[1], st));
+  // offsets are used relative to sig_off[0] on the device
+  if ((rc = launch_verify(curve, n, d_e, d_r, d_s, d_pub, pub_fmt, g.d_status, g.d_ws, st, g.ev[4], g.ev[5], &launches,
+                          d_sig - sig_off[0], d_off))) return rc;
+  CK(cudaEventRecord(g.ev[2], st));
+  CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(g.ev[3], st));
+  CK(cudaStreamSynchronize(st));
+  g.dev_timing_pending = false;
+  g.timing = eb200_timing{};
+  cudaEventElapsedTime(&g.timing.h2d_ms, g.ev[0], g.ev[1]);
+  cudaEventElapsedTime(&g.timing.kernel_ms, g.ev[1], g.ev[2]);
+  cudaEventElapsedTime(&g.timing.d2h_ms, g.ev[2], g.ev[3]);
+  cudaEventElapsedTime(&g.timing.main_kernel_ms, g.ev[4], g.ev[5]);
   g.timing.launches = launches;
   return EB200_OK;
 }

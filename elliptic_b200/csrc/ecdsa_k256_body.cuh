@@ -30,7 +30,7 @@ namespace eb {
 
 enum : uint8_t {
   ST_FALSE = 0, ST_TRUE = 1, ST_THROW_INVALID_POINT = 2, ST_THROW_NOT_VALIDATED = 3,
-  ST_NEEDS_HOST = 4, ST_THROW_ASSERT = 5, ST_THROW_POINT_FORMAT = 6, ST_INFINITY = 7, ST_THROW_SECOND_KEY = 8,
+  ST_NEEDS_HOST = 4, ST_THROW_ASSERT = 5, ST_THROW_POINT_FORMAT = 6, ST_INFINITY = 7, ST_THROW_SECOND_KEY = 8, ST_THROW_SIG_FORMAT = 9,
 };
 
 // workspace layout (SoA, word-major so lanes are coalesced): PREP_WORDS words per item

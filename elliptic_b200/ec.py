@@ -46,6 +46,7 @@ _THROW_MSG = {
     nat.ST_THROW_ASSERT: "Assertion failed",
     nat.ST_THROW_POINT_FORMAT: "Unknown point format",
     nat.ST_THROW_SECOND_KEY: "Unable to find sencond key candinate",
+    nat.ST_THROW_SIG_FORMAT: "Signature without r or s",
 }
 
 
@@ -232,6 +233,20 @@ class EC:
         nat.check(lib.eb200_ecdsa_verify_batch(
             self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data, pub.ctypes.data,
             pub_fmt, status.ctypes.data))
+        return status
+
+    def verify_batch_der_packed(self, e, ders, pub, pub_fmt=nat.PUB_XY):
+        """e: (n, len) uint8 truncated hashes; ders: list of DER byte strings (parsed on the GPU exactly as
+        Signature._importDER, ec/signature.js:73-134); pub: (n, k) uint8 in `pub_fmt`.  Returns statuses."""
+        lib = nat.init(self._device)
+        n = len(ders)
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum([len(d) for d in ders])
+        blob = np.frombuffer(b"".join(bytes(d) for d in ders) + b"\x00", np.uint8)
+        e = np.ascontiguousarray(e, np.uint8); pub = np.ascontiguousarray(pub, np.uint8)
+        status = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_ecdsa_verify_batch_der(self._c["id"], n, e.ctypes.data, blob.ctypes.data, off.ctypes.data,
+                                                   pub.ctypes.data, pub_fmt, status.ctypes.data))
         return status
 
     def verify_batch(self, msgs, sigs, keys, enc=None, msg_bit_length=None):

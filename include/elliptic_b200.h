@@ -43,6 +43,7 @@ extern "C" {
 #define EB200_ST_THROW_POINT_FORMAT 6   /* threw Error('Unknown point format')  base.js:291 */
 #define EB200_ST_INFINITY 7             /* (recover) returned the point at infinity */
 #define EB200_ST_THROW_SECOND_KEY 8     /* (recover) threw Error('Unable to find sencond key candinate')  ec/index.js:244 */
+#define EB200_ST_THROW_SIG_FORMAT 9     /* threw Error('Signature without r or s')  ec/signature.js:15 (DER rejected by _importDER) */
 
 /* curve ids (names of lib/elliptic/curves.js presets) */
 #define EB200_CURVE_SECP256K1 1
@@ -82,6 +83,15 @@ int eb200_last_timing(eb200_timing* out);
 int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r,
                              const uint8_t* s, const uint8_t* pub, uint32_t pub_fmt,
                              uint8_t* status);
+
+/* Same call with the signatures as the reference takes them off the wire: DER (`new Signature(der)`,
+ * lib/elliptic/ec/signature.js:73-134), parsed on the GPU.
+ *   sigs    : the DER encodings back to back
+ *   sig_off : n + 1 byte offsets into `sigs` (item i is sigs[sig_off[i] .. sig_off[i+1]))
+ * status adds THROW_SIG_FORMAT for an encoding _importDER rejects; a key that throws takes precedence
+ * (keyFromPublic runs before new Signature, ec/index.js:194-195). */
+int eb200_ecdsa_verify_batch_der(int curve, size_t n, const uint8_t* e, const uint8_t* sigs, const uint64_t* sig_off,
+                                 const uint8_t* pub, uint32_t pub_fmt, uint8_t* status);
 
 /* Same, with DEVICE pointers and a caller-supplied CUDA stream (cudaStream_t cast to void*;
  * NULL = the CUDA default stream).  Asynchronous: the caller synchronises the stream.

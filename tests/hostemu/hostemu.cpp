@@ -300,3 +300,10 @@ extern "C" void he_drbg_first_k(const uint8_t* priv, const uint8_t* msg, uint8_t
   drbg_first_k(d, m, k);
   for (int w = 0; w < 8; w++) for (int b = 0; b < 4; b++) out[4 * w + b] = (uint8_t)(k[w] >> (24 - 8 * b));
 }
+
+// ---------------------------------------------------------------------------
+// DER signature import (ec/signature.js:73-134)
+#include "../../elliptic_b200/csrc/der_sig.cuh"
+extern "C" int he_der_import(const uint8_t* data, size_t n, size_t len, uint8_t* r, uint8_t* s) {
+  return der_import(data, n, len, r, s) ? 1 : 0;
+}

@@ -284,3 +284,57 @@ def test_mul_and_mul_add_batches(native):
     assert got == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
     got = g.g_mul_batch([c[1] for c in cases])
     assert got == [ref(ec.g.mul(c[1])) for c in cases]
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "p384"])
+def test_der_signatures_parsed_on_gpu(native, name):
+    """eb200_ecdsa_verify_batch_der: DER parsing (ec/signature.js:73-134) on the GPU, then verify.  Every
+    item must get what the reference does with the same bytes: true / false / 'Signature without r or s',
+    and a key that throws must win over a bad signature (ec/index.js:194-195)."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_hostemu_k256 import der_corpus
+    from elliptic_b200.ec import EC as GpuEC
+    from elliptic_b200 import _native as nat
+    from oracle.ref_py.ec import EC
+    from oracle.ref_py.bn import RefError
+    ec = EC(name)
+    ln = (ec.n.bit_length() + 7) // 8
+    rnd = random.Random(21)
+    d = rnd.randrange(1, ec.n)
+    Q = ec.g.mul(d)
+    ders, es = [], []
+    for t in range(120):                                   # well-formed signatures, some over other messages
+        m = rnd.randbytes(ln)
+        sig = ec.sign(m, d)
+        if t % 5 == 4: m = rnd.randbytes(ln)
+        ders.append(bytes(sig.to_der())); es.append(m)
+    for der in der_corpus(seed=9, count=160):
+        ders.append(der); es.append(rnd.randbytes(ln))
+    n = len(ders)
+    e_int = [ec._truncate_to_n(int.from_bytes(m, "big")) for m in es]
+    e = np.frombuffer(b"".join(v.to_bytes(ln, "big") for v in e_int), np.uint8).reshape(n, ln)
+    pub = np.frombuffer((Q.x.to_bytes(ln, "big") + Q.y.to_bytes(ln, "big")) * n, np.uint8).reshape(n, 2 * ln)
+
+    def want(der, m, key):
+        try:
+            return int(ec.verify(m, der, key))
+        except RefError as ex:
+            return {"Signature without r or s": 9, "Unknown point format": 6}[str(ex)]
+
+    st = GpuEC(name).verify_batch_der_packed(e, ders, pub)
+    exp = [want(der, m, {"x": Q.x, "y": Q.y}) for der, m in zip(ders, es)]
+    assert [int(v) for v in st] == exp
+    assert {0, 1, 9} <= set(exp)
+    # compressed keys with a bad tag on every third item: the key's throw wins
+    enc = bytearray(Q.encode(compact=True))
+    keys = []
+    for i in range(n):
+        k = bytearray(enc)
+        if i % 3 == 0: k[0] = 0x05
+        keys.append(bytes(k))
+    pub33 = np.frombuffer(b"".join(keys), np.uint8).reshape(n, ln + 1)
+    st = GpuEC(name).verify_batch_der_packed(e, ders, pub33, nat.PUB_SEC1_33)
+    exp = [want(der, m, list(k)) for der, m, k in zip(ders, es, keys)]
+    assert [int(v) for v in st] == exp
+    assert 6 in exp and 9 in exp

@@ -319,3 +319,47 @@ def test_mul_and_mul_add_bodies_against_oracle(he):
     assert unpack(out, st) == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
     he.he_mul_g(ctypes.c_size_t(n), k2, gp, out, st)
     assert unpack(out, st) == [ref(ec.g.mul(c[1])) for c in cases]
+
+
+def der_corpus(seed=4, count=400):
+    """Valid DER signatures, single-bit corruptions, truncations, long-form lengths, oversize integers."""
+    from oracle.ref_py.signature import Signature
+    rnd = random.Random(seed)
+    out = []
+    for t in range(count):
+        r = rnd.randrange(1, 2 ** rnd.choice([1, 8, 64, 255, 256, 257, 384, 520]))
+        s = rnd.randrange(1, 2 ** rnd.choice([8, 128, 256, 300]))
+        der = bytearray(Signature({"r": r, "s": s}).to_der())
+        k = t % 8
+        if k == 1: der[rnd.randrange(len(der))] ^= 1 << rnd.randrange(8)
+        if k == 2: der = der[:rnd.randrange(len(der))]
+        if k == 3: der += bytes([rnd.randrange(256)])
+        if k == 4: der[1:2] = bytes([0x81, der[1]])                        # long form where short is required
+        if k == 5: der = bytearray(b"\x30\x06\x02\x01\x00\x02\x01\x01")     # r = 0
+        if k == 6: der = bytearray(rnd.randbytes(rnd.randrange(0, 12)))
+        out.append(bytes(der))
+    out += [b"", b"\x30", b"\x30\x00", b"\x30\x02\x02\x00", b"\x30\x04\x02\x00\x02\x00",
+            b"\x30\x84\x00\x00\x00\x08\x02\x02\x00\x80\x02\x02\x00\x81", b"\x30\x81\x88" + b"\x02\x41\x00" + b"\xff" * 64 + b"\x02\x41\x00" + b"\x80" * 64]
+    return out
+
+
+def ref_der(der):
+    from oracle.ref_py.signature import Signature
+    chk = Signature.__new__(Signature)
+    return (chk.r, chk.s) if chk._import_der(der, None) else None
+
+
+def test_der_import_body_matches_reference(he):
+    corpus = der_corpus()
+    kinds = set()
+    for der in corpus:
+        want = ref_der(der)
+        for ln in (32, 48):
+            r, s = (ctypes.c_uint8 * ln)(), (ctypes.c_uint8 * ln)()
+            ok = he.he_der_import(der, ctypes.c_size_t(len(der)), ctypes.c_size_t(ln), r, s)
+            assert bool(ok) == (want is not None), der.hex()
+            if want:
+                fit = lambda v: v if v < 2 ** (8 * ln) else 0
+                assert (int.from_bytes(bytes(r), "big"), int.from_bytes(bytes(s), "big")) == (fit(want[0]), fit(want[1])), der.hex()
+        kinds.add(want is not None)
+    assert kinds == {True, False}
