@@ -24,7 +24,7 @@ EXPORTS = [
     "eb200_eddsa_verify_batch", "eb200_eddsa_verify_workspace_bytes", "eb200_eddsa_verify_batch_dev",
     "eb200_x25519_derive_batch", "eb200_x25519_derive_batch_dev", "eb200_ecdsa_recover_batch", "eb200_ecdsa_sign_batch",
     "eb200_eddsa_verify_batch_msgs", "eb200_scalar_mul_batch", "eb200_mul_add_batch",
-    "eb200_ecdsa_verify_batch_der",
+    "eb200_ecdsa_verify_batch_der", "eb200_ecdh_derive_batch",
 ]
 
 
@@ -70,6 +70,7 @@ def load():
     lib.eb200_ecdsa_sign_batch.argtypes = [c.c_int, c.c_size_t, c.c_void_p, c.c_void_p, c.c_uint32] + [c.c_void_p] * 4
     lib.eb200_ecdsa_recover_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 6
     lib.eb200_ecdsa_verify_batch_der.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4 + [c.c_uint32, c.c_void_p]
+    lib.eb200_ecdh_derive_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4
     lib.eb200_scalar_mul_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 4
     lib.eb200_mul_add_batch.argtypes = [c.c_int, c.c_size_t] + [c.c_void_p] * 5
     lib.eb200_selftest_gtab_dims.argtypes = [c.c_int] + [c.c_void_p] * 3

@@ -139,6 +139,11 @@ k256_mul_g_kernel(size_t N, const uint8_t* __restrict__ k, const u32* __restrict
   status[i] = k256_mul_g_item(i, k, gtab, out);
 }
 
+__global__ void status_map_kernel(size_t N, uint8_t* __restrict__ status, uint8_t from, uint8_t to) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N && status[i] == from) status[i] = to;
+}
+
 // DER signatures -> fixed-width r, s (Signature._importDER, ec/signature.js:73-134).  `pre` carries the
 // key-decoding verdict when there is one: a key that throws wins, as keyFromPublic runs first
 // (ec/index.js:194-195).
@@ -852,7 +857,7 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
 
 template <class C>
 static int sw_mul_add_launch(int curve, size_t n, const uint8_t* d_k1, const uint8_t* d_k2, const uint8_t* d_pts,
-                             uint8_t* d_out, const WsLayout& L, cudaStream_t st, unsigned* launches) {
+                             uint8_t* d_out, const WsLayout& L, cudaStream_t st, unsigned* launches, bool derive) {
   unsigned nb = (unsigned)((n + 127) / 128);
   if (!d_pts) {
     CK(cudaEventRecord(g.ev[4], st));
@@ -868,14 +873,17 @@ static int sw_mul_add_launch(int curve, size_t n, const uint8_t* d_k1, const uin
   sw_mul_add_kernel<C><<<nb, 128, 0, st>>>(n, d_pts, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
   CK(cudaGetLastError());
   CK(cudaEventRecord(g.ev[5], st));
-  sw_mul_add_replay_kernel<C><<<nb, 128, 0, st>>>(n, d_k1, d_k2, d_pts, g.sw_replay_tab[curve], d_out, g.d_status);
+  if (derive) status_map_kernel<<<nb, 128, 0, st>>>(n, g.d_status, ST_NEEDS_HOST, ST_THROW_NOT_VALIDATED);
+  else sw_mul_add_replay_kernel<C><<<nb, 128, 0, st>>>(n, d_k1, d_k2, d_pts, g.sw_replay_tab[curve], d_out, g.d_status);
   CK(cudaGetLastError());
   *launches = 3;
   return EB200_OK;
 }
 
+// derive: KeyPair.derive (ec/key.js:102-107) -- an off-curve point is the reference's
+// 'public point not validated' throw instead of a replayed multiplication, and only x is returned.
 static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts,
-                          uint8_t* out_xy, uint8_t* status) {
+                          uint8_t* out_xy, uint8_t* status, bool derive = false) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
   if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
@@ -898,9 +906,9 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
   if (pts) CK(cudaMemcpyAsync(d_pts, pts, 2 * len * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
   if (curve == EB200_CURVE_P256) {
-    if ((rc = sw_mul_add_launch<P256>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches))) return rc;
+    if ((rc = sw_mul_add_launch<P256>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
   } else if (curve == EB200_CURVE_P384) {
-    if ((rc = sw_mul_add_launch<P384>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches))) return rc;
+    if ((rc = sw_mul_add_launch<P384>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
   } else if (!pts) {
     CK(cudaEventRecord(g.ev[4], st));
     k256_mul_g_kernel<<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
@@ -915,12 +923,14 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
         n, d_pts, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
     CK(cudaGetLastError());
     CK(cudaEventRecord(g.ev[5], st));
-    k256_mul_add_replay_kernel<<<nb, 128, 0, st>>>(n, k1 ? d_k1 : nullptr, d_k2, d_pts, g.replay_tab, d_out, g.d_status);
+    if (derive) status_map_kernel<<<nb, 128, 0, st>>>(n, g.d_status, ST_NEEDS_HOST, ST_THROW_NOT_VALIDATED);
+    else k256_mul_add_replay_kernel<<<nb, 128, 0, st>>>(n, k1 ? d_k1 : nullptr, d_k2, d_pts, g.replay_tab, d_out, g.d_status);
     CK(cudaGetLastError());
     launches = 3;
   }
   CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(out_xy, d_out, 2 * len * n, cudaMemcpyDeviceToHost, st));
+  if (derive) CK(cudaMemcpy2DAsync(out_xy, len, d_out, 2 * len, len, n, cudaMemcpyDeviceToHost, st));   // x only
+  else CK(cudaMemcpyAsync(out_xy, d_out, 2 * len * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(g.ev[3], st));
   CK(cudaStreamSynchronize(st));
@@ -939,6 +949,12 @@ extern "C" {
 int eb200_scalar_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* points_xy, uint8_t* out_xy,
                            uint8_t* status) {
   return mul_add_common(curve, n, nullptr, k, points_xy, out_xy, status);
+}
+
+int eb200_ecdh_derive_batch(int curve, size_t n, const uint8_t* priv, const uint8_t* pub_xy, uint8_t* out_x,
+                            uint8_t* status) {
+  if (n && !pub_xy) return EB200_ERR_ARG;
+  return mul_add_common(curve, n, nullptr, priv, pub_xy, out_x, status, true);
 }
 
 int eb200_mul_add_batch(int curve, size_t n, const uint8_t* k1, const uint8_t* k2, const uint8_t* p2_xy,

@@ -410,7 +410,7 @@ class EC:
         (ec/key.js:76-82, 102-107) on curve25519.  privs: ints / hex / bytes; pubs: the peer's x as
         int / hex / big-endian bytes (mont.js:46-48).  Returns (list of int-or-None, statuses)."""
         if self.name != "curve25519":
-            raise EllipticError("derive_batch: only curve25519 is accelerated")
+            return self._derive_short(privs, pubs)
         lib = nat.init(self._device)
         n = len(privs)
         k = np.zeros((n, 32), np.uint8)
@@ -425,6 +425,18 @@ class EC:
         out = np.zeros((n, 32), np.uint8)
         st = np.zeros(n, np.uint8)
         nat.check(lib.eb200_x25519_derive_batch(n, k.ctypes.data, x.ctypes.data, out.ctypes.data, st.ctypes.data))
+        vals = [int.from_bytes(out[i].tobytes(), "big") if st[i] == nat.ST_TRUE else None for i in range(n)]
+        return vals, st
+
+    def _derive_short(self, privs, pubs):
+        """Short curves: pubs are the peer's points as {x, y} / (x, y) (keyFromPublic(...).getPublic())."""
+        lib = nat.init(self._device)
+        n, ln = len(privs), self._len
+        k = self._scalars([_bn(p) % self.n for p in privs])
+        pts = self._points(pubs)
+        out = np.zeros((n, ln), np.uint8)
+        st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_ecdh_derive_batch(self._c["id"], n, k.ctypes.data, pts.ctypes.data, out.ctypes.data, st.ctypes.data))
         vals = [int.from_bytes(out[i].tobytes(), "big") if st[i] == nat.ST_TRUE else None for i in range(n)]
         return vals, st
 

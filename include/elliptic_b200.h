@@ -130,6 +130,15 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
 int eb200_scalar_mul_batch(int curve, size_t n, const uint8_t* k, const uint8_t* points_xy, uint8_t* out_xy,
                            uint8_t* status);
 
+/* Batch of KeyPair.prototype.derive (lib/elliptic/ec/key.js:102-107) on the short curves: ECDH shared x.
+ *   priv   : n x len private scalars, big-endian (reduced mod n as _importPrivate does, ec/key.js:76-82)
+ *   pub_xy : n x 2len peer points x || y
+ *   out_x  : n x len  pub.mul(priv).getX(), big-endian (zeroed unless status is TRUE)
+ * status: TRUE, THROW_NOT_VALIDATED (the peer point is not on the curve), INFINITY (priv = 0 mod n: the
+ * reference then dies with a TypeError inside getX()).  curve25519 has its own entry point below. */
+int eb200_ecdh_derive_batch(int curve, size_t n, const uint8_t* priv, const uint8_t* pub_xy, uint8_t* out_x,
+                            uint8_t* status);
+
 /* Batch of G.mulAdd(k1, P2, k2) = k1*G + k2*P2 (lib/elliptic/curve/short.js:434-441; _endoWnafMulAdd
  * short.js:218-249 on secp256k1, _wnafMulAdd base.js:128-253 on p256 / p384).  Arguments and status as
  * eb200_scalar_mul_batch. */

@@ -204,3 +204,30 @@ def test_mul_and_mul_add_batches(native, name):
         [ref(ec.g.mul_add(c[0], ec.curve.point(c[2], c[3]), c[1])) for c in cases]
     assert g.mul_batch(pts, [c[1] for c in cases]) == [ref(ec.curve.point(c[2], c[3]).mul(c[1])) for c in cases]
     assert g.g_mul_batch([c[1] for c in cases]) == [ref(ec.g.mul(c[1])) for c in cases]
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "p256", "p384"])
+def test_ecdh_derive_on_short_curves(native, name):
+    """KeyPair.derive (ec/key.js:102-107; test/ecdh-test.js:8-43): shared x equals the oracle's, both
+    sides agree, and the twist-attack point {x: 14, y: 16} is refused with the reference's message."""
+    from elliptic_b200.ec import EC as GpuEC, EllipticError
+    from oracle.ref_py.ec import EC
+    ec, g = EC(name), GpuEC(name)
+    rnd = random.Random(17)
+    privs = [rnd.randrange(1, ec.n) for _ in range(40)] + [1, ec.n - 1, ec.n + 5]
+    peers = [ec.g.mul(rnd.randrange(1, ec.n)) for _ in range(len(privs))]
+    pubs = [{"x": q.x, "y": q.y} for q in peers]
+    pubs[3] = {"x": 14, "y": 16}
+    pubs[5] = {"x": peers[5].x, "y": (peers[5].y + 1) % ec.curve.p}
+    vals, st = g.derive_batch(privs, pubs)
+    for i, (d, pb) in enumerate(zip(privs, pubs)):
+        pt = ec.curve.point(pb["x"], pb["y"])
+        if not ec.curve.validate(pt):
+            assert (int(st[i]), vals[i]) == (3, None)
+        else:
+            assert (int(st[i]), vals[i]) == (1, ec.key_from_private(d % ec.n).derive(pt)), i
+    a, b = privs[0], privs[1]
+    A, B = g.g_mul_batch([a, b])
+    assert g.derive(a, {"x": B[0], "y": B[1]}) == g.derive(b, {"x": A[0], "y": A[1]})
+    with pytest.raises(EllipticError, match="public point not validated"):
+        g.derive(a, {"x": 14, "y": 16})
