@@ -141,6 +141,15 @@ static void run(const char* name, int sms, u32* d_a, u32* d_b) {
   cudaMemcpy(hb, d_b, words * 4, cudaMemcpyDeviceToHost);
   size_t bad = 0;
   for (size_t i = 0; i < words; i++) bad += ha[i] != hb[i];
+  if (bad) {   // diagnostic: the first differing item, limb by limb
+    size_t it = 0;
+    for (size_t i = 0; i < words; i++) if (ha[i] != hb[i]) { it = i / N; break; }
+    fprintf(stderr, "%s first differing item %zu\n thread:", name, it);
+    for (int i = 0; i < N; i++) fprintf(stderr, " %08x", ha[it * N + i]);
+    fprintf(stderr, "\n warp:  ");
+    for (int i = 0; i < N; i++) fprintf(stderr, " %08x", hb[it * N + i]);
+    fprintf(stderr, "\n");
+  }
   free(ha); free(hb);
   double best_t = 0, best_w = 0;
   int cfgs[][2] = {{4, 128}, {4, 256}, {8, 128}, {2, 512}};

@@ -17,6 +17,14 @@ namespace eb {
 constexpr int SIGN_WS_WORDS = 32;      // per item: X, Y, Z, k (8 words each), word-major SoA
 constexpr int SIGN_SCRATCH_WORDS = 16; // per item: prefix products of Z and of k
 
+EB_HD void eb_prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 EB_HD void sha256_compress_w(u32* st, const u32* win) {
   u32 w[16];
 #pragma unroll
@@ -158,6 +166,9 @@ EB_HD void k256_sign_nonce_item(size_t i, size_t N, const uint8_t* e, const uint
     if (negg) sub_n<8>(kk, nn, kk);
     u32 m[8];
     for (int w = 0; w < 8; w++) m[w] = (kk[w] >> 1) | ((w < 7 ? kk[w + 1] : 0u) << 31);
+    // all table addresses are known up front: compute them, prefetch the (HBM-resident) entries, then add
+    const u32* ent[GTAB_WINDOWS];
+    u32 negmask = 0;
     for (int j = 0; j < GTAB_WINDOWS; j++) {
       const int pos = GTAB_W * j;
       u32 lo = 0, hi = 0;
@@ -167,11 +178,15 @@ EB_HD void k256_sign_nonce_item(size_t i, size_t N, const uint8_t* e, const uint
       const u32 half = 1u << (GTAB_W - 1);
       bool dneg = (j != GTAB_WINDOWS - 1) && (chunk < half);
       u32 idx = (j == GTAB_WINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
-      const u32* ent = gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16;
+      ent[j] = gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16;
+      eb_prefetch_l2(ent[j]);
+      if (dneg != negg) negmask |= 1u << j;
+    }
+    for (int j = 0; j < GTAB_WINDOWS; j++) {
       ge_aff P;
-      P.x = load_fe(ent);
-      P.y = load_fe(ent + 8);
-      acc = jac_madd(acc, aff_neg_if(P, dneg != negg));
+      P.x = load_fe(ent[j]);
+      P.y = load_fe(ent[j] + 8);
+      acc = jac_madd(acc, aff_neg_if(P, (negmask >> j) & 1));
     }
   }
   for (int w = 0; w < 8; w++) {
