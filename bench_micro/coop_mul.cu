@@ -66,7 +66,7 @@ __device__ __forceinline__ u32 coop_mul(u32 a, u32 b, u32 p, u32 n0inv, int lane
   {
     u32 G = (__ballot_sync(full, c1 != 0) >> gbase) & gmask;
     u32 Pm = (__ballot_sync(full, digit == 0xffffffffu) >> gbase) & gmask;
-    u32 Gs = (G << 1), X = (Pm | Gs), Y = Gs;                  // carry of lane j enters lane j+1
+    u32 X = (Pm | G), Y = G;                                   // bit j of (X + Y) ^ X ^ Y = carry into lane j
     u32 sum = X + Y;
     u32 cin = sum ^ X ^ Y;
     digit += (cin >> lane) & 1;
@@ -78,7 +78,7 @@ __device__ __forceinline__ u32 coop_mul(u32 a, u32 b, u32 p, u32 n0inv, int lane
   {
     u32 G = (__ballot_sync(full, digit < p) >> gbase) & gmask;
     u32 Pm = (__ballot_sync(full, digit == p) >> gbase) & gmask;
-    u32 Gs = (G << 1), X = (Pm | Gs), Y = Gs;
+    u32 X = (Pm | G), Y = G;
     u32 sum = X + Y;
     u32 bin = sum ^ X ^ Y;
     d -= (bin >> lane) & 1;
