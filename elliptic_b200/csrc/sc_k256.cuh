@@ -15,6 +15,7 @@
 // all the reference's result depends on (off-curve keys: see ecdsa_k256.cu).
 #pragma once
 #include "limbs.cuh"
+#include "fp_mont.cuh"
 
 namespace eb {
 
@@ -36,8 +37,28 @@ struct K256N {
   static constexpr u32 n0inv = 0x5588b13fu;  // -n^-1 mod 2^32
 };
 
+// the same constants in the shape fp_mont.cuh's generic field wants
+struct K256_FN {
+  static constexpr int N = 8;
+  static constexpr u32 n0inv = K256N::n0inv;
+  static EB_HD void mod(u32* r) { K256N::n(r); }
+  static EB_HD void r1(u32* r) { K256N::r1(r); }
+  static EB_HD void r2(u32* r) { K256N::r2(r); }
+};
+
 // Montgomery product a*b*2^-256 mod n (CIOS); a < 2^256, b < n -> result < n.
+// Device: the out-of-line two-accumulator PTX multiplier of fp_mont.cuh; host: the portable loop below.
 EB_HD void sc_mont_mul(u32* r, const u32* a, const u32* b) {
+#if defined(__CUDA_ARCH__)
+  typedef Fp<K256_FN> S;
+  S::fe x, y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  S::fe z = S::mul(x, y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+  return;
+#endif
   u32 n[8]; K256N::n(n);
   u32 t[10];
 #pragma unroll
