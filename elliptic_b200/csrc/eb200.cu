@@ -1178,16 +1178,18 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
   size_t bytes = n * fe_len(curve);
   u32 *da, *db, *dout;
   CK(cudaMalloc(&da, bytes)); CK(cudaMalloc(&db, bytes)); CK(cudaMalloc(&dout, bytes));
-  CK(cudaMemcpy(da, a, bytes, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(db, b, bytes, cudaMemcpyHostToDevice));
+  // stream-ordered copies: a synchronous cudaMemcpy from pageable memory may return before its DMA lands,
+  // and g.stream (non-blocking) does not wait for the legacy default stream
+  CK(cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, g.stream));
+  CK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, g.stream));
   unsigned nb = (unsigned)((n + 127) / 128);
   if (curve == EB200_CURVE_SECP256K1) k256_selftest_fe_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_P256) sw_selftest_fe_kernel<P256><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_ED25519 || curve == EB200_CURVE_CURVE25519) f25_selftest_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else sw_selftest_fe_kernel<P384><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
-  CK(cudaMemcpy(out, dout, bytes, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return EB200_OK;
 }
@@ -1211,7 +1213,8 @@ int eb200_selftest_gtab(int curve, uint32_t* out, size_t n_words) {
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
   if ((rc = ensure_table(curve))) return rc;
-  CK(cudaMemcpy(out, g.gtab[curve], words * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpyAsync(out, g.gtab[curve], words * 4, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
   return EB200_OK;
 }
 
