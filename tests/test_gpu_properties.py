@@ -146,3 +146,31 @@ def test_curve25519_ecdh_agreement(native):
         o = np.zeros((1, 32), np.uint8); s1 = np.zeros(1, np.uint8)
         nat.check(lib.eb200_x25519_derive_batch(1, kb.ctypes.data, px.ctypes.data, o.ctypes.data, s1.ctypes.data))
         assert s1[0] == 1 and o[0].tobytes()[::-1] == want
+
+
+@pytest.mark.parametrize("name", ["secp256k1", "p256", "p384"])
+def test_openssl_signatures_verify_and_forgeries_do_not(native, name):
+    """Independent implementation as the producer: 2^12 ECDSA signatures made by OpenSSL (`cryptography`)
+    must all verify through the C ABI -- with DER signatures and SEC1 keys straight off the wire, parsed on
+    the GPU -- and none may verify once the digest is altered."""
+    from cryptography.hazmat.primitives.asymmetric import ec as cec, utils as cutils
+    from cryptography.hazmat.primitives import hashes, serialization as ser
+    from elliptic_b200.ec import EC as GpuEC
+    from elliptic_b200 import _native as nat
+    curve, h, ln = {"secp256k1": (cec.SECP256K1(), hashes.SHA256(), 32), "p256": (cec.SECP256R1(), hashes.SHA256(), 32),
+                    "p384": (cec.SECP384R1(), hashes.SHA384(), 48)}[name]
+    rnd = random.Random(99)
+    keys = [cec.generate_private_key(curve) for _ in range(16)]
+    pubs65 = [k.public_key().public_bytes(ser.Encoding.X962, ser.PublicFormat.UncompressedPoint) for k in keys]
+    pubs33 = [k.public_key().public_bytes(ser.Encoding.X962, ser.PublicFormat.CompressedPoint) for k in keys]
+    n = 1 << 12
+    digests = [rnd.randbytes(ln) for _ in range(n)]
+    ders = [keys[i % 16].sign(digests[i], cec.ECDSA(cutils.Prehashed(h))) for i in range(n)]
+    g = GpuEC(name)
+    e = np.frombuffer(b"".join(digests), np.uint8).reshape(n, ln)          # digest length = n's byte length: no shift
+    for fmt, pubs in ((nat.PUB_SEC1_65, pubs65), (nat.PUB_SEC1_33, pubs33)):
+        pub = np.frombuffer(b"".join(pubs[i % 16] for i in range(n)), np.uint8).reshape(n, -1)
+        st = g.verify_batch_der_packed(e, ders, pub, fmt)
+        assert (st == 1).all(), np.nonzero(st != 1)[0][:5]
+        e2 = e.copy(); e2[:, ln - 1] ^= 0x10
+        assert (g.verify_batch_der_packed(e2, ders, pub, fmt) == 0).all()
