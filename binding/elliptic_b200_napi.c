@@ -86,10 +86,106 @@ static napi_value X25519DeriveBatch(napi_env env, napi_callback_info info) {
   return argv[2];
 }
 
+static size_t field_len(int curve) { return curve == EB200_CURVE_P384 ? 48 : 32; }
+
+/* ecdsaVerifyBatchDer(curveId, e, sigs, sigOff (n + 1 little-endian u64 offsets, as a Uint8Array view), pub, pubFmt) -> Uint8Array(n)
+ * DER signatures as `new Signature(der)` takes them (ec/signature.js:73-134), parsed on the GPU */
+static napi_value EcdsaVerifyBatchDer(napi_env env, napi_callback_info info) {
+  size_t argc = 6; napi_value argv[6];
+  napi_get_cb_info(env, info, &argc, argv, 0, 0);
+  int32_t curve; uint32_t fmt; uint8_t *e, *sig, *off, *pub, *st; size_t le, lsg, lo, lp;
+  if (argc < 6 || napi_get_value_int32(env, argv[0], &curve) != napi_ok || !u8(env, argv[1], &e, &le) ||
+      !u8(env, argv[2], &sig, &lsg) || !u8(env, argv[3], &off, &lo) || !u8(env, argv[4], &pub, &lp) ||
+      napi_get_value_uint32(env, argv[5], &fmt) != napi_ok)
+    return fail(env, EB200_ERR_ARG);
+  size_t n = le / field_len(curve);
+  if (lo != 8 * (n + 1)) return fail(env, EB200_ERR_ARG);
+  napi_value arr = out_u8(env, n, &st);
+  int rc = eb200_ecdsa_verify_batch_der(curve, n, e, sig, (const uint64_t*)off, pub, fmt, st);
+  return rc ? fail(env, rc) : arr;
+}
+
+/* ecdsaSignBatch(curveId, e, priv, flags, result) -> result {r, s, recid, status}
+ * (EC.prototype.sign with RFC 6979 nonces, ec/index.js:110-186) */
+static napi_value EcdsaSignBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 5; napi_value argv[5];
+  napi_get_cb_info(env, info, &argc, argv, 0, 0);
+  int32_t curve; uint32_t flags; uint8_t *e, *d, *r, *s, *id, *st; size_t le, ld;
+  if (argc < 5 || napi_get_value_int32(env, argv[0], &curve) != napi_ok || !u8(env, argv[1], &e, &le) ||
+      !u8(env, argv[2], &d, &ld) || napi_get_value_uint32(env, argv[3], &flags) != napi_ok || le % 32 || ld != le)
+    return fail(env, EB200_ERR_ARG);
+  size_t n = le / 32;
+  napi_value ar = out_u8(env, le, &r), as = out_u8(env, le, &s), ai = out_u8(env, n, &id), ast = out_u8(env, n, &st);
+  int rc = eb200_ecdsa_sign_batch(curve, n, e, d, flags, r, s, id, st);
+  if (rc) return fail(env, rc);
+  napi_set_named_property(env, argv[4], "r", ar);
+  napi_set_named_property(env, argv[4], "s", as);
+  napi_set_named_property(env, argv[4], "recid", ai);
+  napi_set_named_property(env, argv[4], "status", ast);
+  return argv[4];
+}
+
+/* ecdsaRecoverBatch(curveId, e, r, s, recid, result) -> result {pub, status}   (recoverPubKey, ec/index.js:231-259) */
+static napi_value EcdsaRecoverBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 6; napi_value argv[6];
+  napi_get_cb_info(env, info, &argc, argv, 0, 0);
+  int32_t curve; uint8_t *e, *r, *s, *id, *out, *st; size_t le, lr, ls, li;
+  if (argc < 6 || napi_get_value_int32(env, argv[0], &curve) != napi_ok || !u8(env, argv[1], &e, &le) ||
+      !u8(env, argv[2], &r, &lr) || !u8(env, argv[3], &s, &ls) || !u8(env, argv[4], &id, &li) || le % 32 ||
+      lr != le || ls != le || li != le / 32)
+    return fail(env, EB200_ERR_ARG);
+  size_t n = le / 32;
+  napi_value ao = out_u8(env, 64 * n, &out), ast = out_u8(env, n, &st);
+  int rc = eb200_ecdsa_recover_batch(curve, n, e, r, s, id, out, st);
+  if (rc) return fail(env, rc);
+  napi_set_named_property(env, argv[5], "pub", ao);
+  napi_set_named_property(env, argv[5], "status", ast);
+  return argv[5];
+}
+
+/* mulAddBatch(curveId, k1 | null, k2, points | null, result) -> result {points, status}
+ * k1 null: Point.mul (short.js:422-432); points null: G.mul; both given: G.mulAdd(k1, P, k2) (short.js:434-441) */
+static napi_value MulAddBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 5; napi_value argv[5];
+  napi_get_cb_info(env, info, &argc, argv, 0, 0);
+  int32_t curve; uint8_t *k1 = 0, *k2, *pts = 0, *out, *st; size_t l1 = 0, l2, lp = 0;
+  if (argc < 5 || napi_get_value_int32(env, argv[0], &curve) != napi_ok || !u8(env, argv[2], &k2, &l2))
+    return fail(env, EB200_ERR_ARG);
+  u8(env, argv[1], &k1, &l1);          /* null / undefined leave the pointer at 0 */
+  u8(env, argv[3], &pts, &lp);
+  size_t len = field_len(curve), n = l2 / len;
+  if (l2 != n * len || (k1 && l1 != l2) || (pts && lp != 2 * l2) || (k1 && !pts)) return fail(env, EB200_ERR_ARG);
+  napi_value ao = out_u8(env, 2 * len * n, &out), ast = out_u8(env, n, &st);
+  int rc = k1 ? eb200_mul_add_batch(curve, n, k1, k2, pts, out, st) : eb200_scalar_mul_batch(curve, n, k2, pts, out, st);
+  if (rc) return fail(env, rc);
+  napi_set_named_property(env, argv[4], "points", ao);
+  napi_set_named_property(env, argv[4], "status", ast);
+  return argv[4];
+}
+
+/* ecdhDeriveBatch(curveId, priv, pubXY, result) -> result {out, status}   (KeyPair.derive, ec/key.js:102-107) */
+static napi_value EcdhDeriveBatch(napi_env env, napi_callback_info info) {
+  size_t argc = 4; napi_value argv[4];
+  napi_get_cb_info(env, info, &argc, argv, 0, 0);
+  int32_t curve; uint8_t *k, *pts, *out, *st; size_t lk, lp;
+  if (argc < 4 || napi_get_value_int32(env, argv[0], &curve) != napi_ok || !u8(env, argv[1], &k, &lk) ||
+      !u8(env, argv[2], &pts, &lp) || lk % field_len(curve) || lp != 2 * lk)
+    return fail(env, EB200_ERR_ARG);
+  size_t n = lk / field_len(curve);
+  napi_value ao = out_u8(env, lk, &out), ast = out_u8(env, n, &st);
+  int rc = eb200_ecdh_derive_batch(curve, n, k, pts, out, st);
+  if (rc) return fail(env, rc);
+  napi_set_named_property(env, argv[3], "out", ao);
+  napi_set_named_property(env, argv[3], "status", ast);
+  return argv[3];
+}
+
 static napi_value Register(napi_env env, napi_value exports) {
   static const struct { const char* name; napi_callback cb; } fns[] = {
       {"init", Init}, {"ecdsaVerifyBatch", EcdsaVerifyBatch}, {"eddsaVerifyBatch", EddsaVerifyBatch},
-      {"x25519DeriveBatch", X25519DeriveBatch}};
+      {"x25519DeriveBatch", X25519DeriveBatch}, {"ecdsaVerifyBatchDer", EcdsaVerifyBatchDer},
+      {"ecdsaSignBatch", EcdsaSignBatch}, {"ecdsaRecoverBatch", EcdsaRecoverBatch}, {"mulAddBatch", MulAddBatch},
+      {"ecdhDeriveBatch", EcdhDeriveBatch}};
   for (unsigned i = 0; i < sizeof fns / sizeof fns[0]; i++) {
     napi_value f;
     napi_create_function(env, fns[i].name, (size_t)-1, fns[i].cb, 0, &f);
