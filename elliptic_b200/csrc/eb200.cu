@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint
   typedef SW<C> W;
   typedef typename W::F F;
   constexpr int NL = W::N;
-  constexpr size_t LEN = 4 * NL;
+  constexpr size_t LEN = C::LEN;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   uint8_t st = 0;
@@ -304,10 +304,10 @@ __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint
     uint8_t tag = p[0];
     if (tag != 2 && tag != 3) st = ST_THROW_POINT_FORMAT;
     typename F::fe t;
-    load_be<NL>(t.v, p + 1);
+    W::ldb(t.v, p + 1);
     typename F::fe x = F::to_mont(t);
     typename F::fe y2 = F::add(F::sub(F::mul(F::sqr(x), x), F::add(F::dbl(x), x)), C::b());
-    u32 e[NL]; F::Params::mod(e);                     // (p+1)/4: p = 3 mod 4 for p256 and p384
+    u32 e[NL]; F::Params::mod(e);                     // (p+1)/4: p = 3 mod 4 for p256, p384 and p521
     { u32 one[NL] = {1}; add_n<NL>(e, e, one); }
     for (int k = 0; k < NL; k++) e[k] = (e[k] >> 2) | ((k + 1 < NL ? e[k + 1] : 0u) << 30);
     typename F::fe y = F::pow(y2, e);
@@ -316,8 +316,8 @@ __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint
     bool odd = tag == 3;
     if (((yp.v[0] & 1) != 0) != odd) yp = F::from_mont(F::neg(y));
     typename F::fe xp = F::from_mont(x);
-    store_be<NL>(xy + 2 * LEN * i, xp.v);
-    store_be<NL>(xy + 2 * LEN * i + LEN, yp.v);
+    W::stb(xy + 2 * LEN * i, xp.v);
+    W::stb(xy + 2 * LEN * i + LEN, yp.v);
   }
   pre[i] = st;
 }
@@ -427,12 +427,14 @@ int grow(uint8_t** p, size_t* cap, size_t need) {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t fe_len(int curve) {   // field-element bytes for the selftest hooks (also the 25519 curves)
-  return (curve == EB200_CURVE_P384) ? 48 : (curve >= EB200_CURVE_SECP256K1 && curve <= EB200_CURVE_CURVE25519) ? 32 : 0;
+  return (curve == EB200_CURVE_P384) ? 48 : (curve == EB200_CURVE_P521) ? 72 :     // 18 limbs
+         (curve >= EB200_CURVE_SECP256K1 && curve <= EB200_CURVE_CURVE25519) ? 32 : 0;
 }
 size_t curve_len(int curve) {
   switch (curve) {
     case EB200_CURVE_SECP256K1: case EB200_CURVE_P256: return 32;
     case EB200_CURVE_P384: return 48;
+    case EB200_CURVE_P521: return 66;
     default: return 0;
   }
 }
@@ -446,7 +448,8 @@ WsLayout ws_layout(int curve, size_t n) {
   size_t prep_words, scratch_words, qtab_words, len = curve_len(curve);
   if (curve == EB200_CURVE_SECP256K1) { prep_words = PREP_WORDS; scratch_words = 8; qtab_words = QTAB_WORDS; }
   else if (curve == EB200_CURVE_P256) { prep_words = SW<P256>::PREP_WORDS; scratch_words = 8; qtab_words = SW<P256>::QTAB_WORDS; }
-  else { prep_words = SW<P384>::PREP_WORDS; scratch_words = 12; qtab_words = SW<P384>::QTAB_WORDS; }
+  else if (curve == EB200_CURVE_P384) { prep_words = SW<P384>::PREP_WORDS; scratch_words = 12; qtab_words = SW<P384>::QTAB_WORDS; }
+  else { prep_words = SW<P521>::PREP_WORDS; scratch_words = 18; qtab_words = SW<P521>::QTAB_WORDS; }
   WsLayout L;
   L.ws = 0;
   L.scratch = align256(L.ws + prep_words * n * 4);
@@ -486,6 +489,7 @@ int ensure_table(int curve) {
   }
   if (curve == EB200_CURVE_P256) return sw_ensure_table<P256>(curve);
   if (curve == EB200_CURVE_P384) return sw_ensure_table<P384>(curve);
+  if (curve == EB200_CURVE_P521) return sw_ensure_table<P521>(curve);
   if (curve == EB200_CURVE_ED25519) {
     if (g.gtab[curve]) return EB200_OK;
     size_t entries = (size_t)ED_GWINDOWS * ED_GENTRIES;
@@ -496,6 +500,20 @@ int ensure_table(int curve) {
     return EB200_OK;
   }
   return EB200_ERR_UNSUPPORTED;
+}
+
+template <class C>
+int sw_launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, const uint8_t* d_s, const uint8_t* xy,
+                     const uint8_t* pre, u32* ws, u32* scratch, u32* qtab, uint8_t* d_status, cudaStream_t st,
+                     unsigned pb, unsigned nb, cudaEvent_t ev_main0, cudaEvent_t* ev_main1) {
+  sw_prep_kernel<C><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
+  CK(cudaGetLastError());
+  if (ev_main0) CK(cudaEventRecord(ev_main0, st));
+  sw_verify_kernel<C><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
+  CK(cudaGetLastError());
+  if (*ev_main1) { CK(cudaEventRecord(*ev_main1, st)); *ev_main1 = nullptr; }
+  sw_replay_kernel<C><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.sw_replay_tab[curve], d_status);
+  return EB200_OK;
 }
 
 // Launches decode (if needed) + prep + verify for n items on stream st.  All pointers are device pointers.
@@ -519,7 +537,8 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     uint8_t* dpre = d_workspace + L.pre;
     if (curve == EB200_CURVE_SECP256K1) k256_decode_pub_kernel<<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
     else if (curve == EB200_CURVE_P256) sw_decode_pub_kernel<P256><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
-    else sw_decode_pub_kernel<P384><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    else if (curve == EB200_CURVE_P384) sw_decode_pub_kernel<P384><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    else sw_decode_pub_kernel<P521><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
     CK(cudaGetLastError());
     xy = dxy; pre = dpre; cnt++;
   }
@@ -539,23 +558,11 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
     k256_replay_kernel<<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.replay_tab, d_status);
     cnt++;
-  } else if (curve == EB200_CURVE_P256) {
-    sw_prep_kernel<P256><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
-    CK(cudaGetLastError());
-    if (ev_main0) CK(cudaEventRecord(ev_main0, st));
-    sw_verify_kernel<P256><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
-    CK(cudaGetLastError());
-    if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
-    sw_replay_kernel<P256><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.sw_replay_tab[curve], d_status);
-    cnt++;
   } else {
-    sw_prep_kernel<P384><<<pb, 128, 0, st>>>(n, d_e, d_r, d_s, ws, scratch);
-    CK(cudaGetLastError());
-    if (ev_main0) CK(cudaEventRecord(ev_main0, st));
-    sw_verify_kernel<P384><<<nb, 128, 0, st>>>(n, xy, d_r, ws, g.gtab[curve], qtab, pre, d_status);
-    CK(cudaGetLastError());
-    if (ev_main1) { CK(cudaEventRecord(ev_main1, st)); ev_main1 = nullptr; }
-    sw_replay_kernel<P384><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.sw_replay_tab[curve], d_status);
+    int rc = curve == EB200_CURVE_P256 ? sw_launch_verify<P256>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1)
+           : curve == EB200_CURVE_P384 ? sw_launch_verify<P384>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1)
+                                       : sw_launch_verify<P521>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1);
+    if (rc) return rc;
     cnt++;
   }
   CK(cudaGetLastError());
@@ -909,6 +916,8 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
     if ((rc = sw_mul_add_launch<P256>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
   } else if (curve == EB200_CURVE_P384) {
     if ((rc = sw_mul_add_launch<P384>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
+  } else if (curve == EB200_CURVE_P521) {
+    if ((rc = sw_mul_add_launch<P521>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
   } else if (!pts) {
     CK(cudaEventRecord(g.ev[4], st));
     k256_mul_g_kernel<<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
@@ -1186,6 +1195,7 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
   if (curve == EB200_CURVE_SECP256K1) k256_selftest_fe_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_P256) sw_selftest_fe_kernel<P256><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_ED25519 || curve == EB200_CURVE_CURVE25519) f25_selftest_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
+  else if (curve == EB200_CURVE_P521) sw_selftest_fe_kernel<P521><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else sw_selftest_fe_kernel<P384><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, g.stream));
@@ -1199,6 +1209,7 @@ int eb200_selftest_gtab_dims(int curve, int* windows, int* entries, int* wbits) 
   if (curve == EB200_CURVE_SECP256K1) { *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W; }
   else if (curve == EB200_CURVE_P256) { *windows = SW<P256>::GWINDOWS; *entries = SW<P256>::GENTRIES; *wbits = SW<P256>::GW; }
   else if (curve == EB200_CURVE_P384) { *windows = SW<P384>::GWINDOWS; *entries = SW<P384>::GENTRIES; *wbits = SW<P384>::GW; }
+  else if (curve == EB200_CURVE_P521) { *windows = SW<P521>::GWINDOWS; *entries = SW<P521>::GENTRIES; *wbits = SW<P521>::GW; }
   else return EB200_ERR_UNSUPPORTED;
   return EB200_OK;
 }
@@ -1208,7 +1219,7 @@ int eb200_selftest_gtab(int curve, uint32_t* out, size_t n_words) {
   int w, en, b;
   int rc = eb200_selftest_gtab_dims(curve, &w, &en, &b);
   if (rc) return rc;
-  size_t words = (size_t)w * en * 2 * (curve_len(curve) / 4);
+  size_t words = (size_t)w * en * 2 * (fe_len(curve) / 4);
   if (!out || n_words < words) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));

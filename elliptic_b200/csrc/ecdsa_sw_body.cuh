@@ -23,16 +23,24 @@ struct SW {
   struct aff { fe x, y; };
 
   static constexpr int MBITS = C::BITS - 1;                  // bits of m = (u'-1)/2
-  static constexpr int QWINDOWS = (MBITS + 3) / 4;
+  static constexpr int QWINDOWS = MBITS / 4 + 1;              // the top digit then has at most 3 bits
   static_assert(MBITS - 4 * (QWINDOWS - 1) <= 3, "top 4-bit digit must stay positive");
   static constexpr int GW = C::GW;
-  static constexpr int GWINDOWS = (MBITS + GW - 1) / GW;
+  static constexpr int GWINDOWS = MBITS / GW + 1;
   static constexpr int GENTRIES = 1 << (GW - 1);
   static_assert(MBITS - GW * (GWINDOWS - 1) <= GW - 1, "top fixed-base digit must stay positive");
   static constexpr int PREP_WORDS = 2 * N + 1;               // mG[N], m2[N], flags
   static constexpr int QTAB_WORDS = 8 * 3 * N;               // 8 Jacobian entries
   static constexpr int BATCH = 16;
   static constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG2 = 4, FL_NOG = 8;
+
+  // field-sized big-endian strings: 4N bytes, except p521 (66 bytes in 18 limbs)
+  static EB_HD void ldb(u32* r, const uint8_t* p) {
+    if (C::LEN == 4 * N) load_be<N>(r, p); else load_be_len<N>(r, p, C::LEN);
+  }
+  static EB_HD void stb(uint8_t* p, const u32* a) {
+    if (C::LEN == 4 * N) store_be<N>(p, a); else store_be_len<N>(p, a, C::LEN);
+  }
 
   static EB_HD jac infinity() { jac r; r.x = F::one(); r.y = F::one(); r.z = F::zero(); return r; }
   static EB_HD jac from_aff(const aff& p) { jac r; r.x = p.x; r.y = p.y; r.z = F::one(); return r; }
@@ -147,7 +155,7 @@ struct SW {
   static EB_HD void prep_thread(size_t tid, size_t T, size_t cnt_items, const uint8_t* e, const uint8_t* r,
                                 const uint8_t* s, u32* ws, u32* scratch) {
     typedef typename S::fe sc;
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 nmod[N];
     n_limbs(nmod);
     sc prod = S::one();
@@ -158,8 +166,8 @@ struct SW {
       if (i >= cnt_items) break;
       cnt = j + 1;
       sc sv, rv;
-      load_be<N>(sv.v, s + LEN * i);
-      load_be<N>(rv.v, r + LEN * i);
+      ldb(sv.v, s + LEN * i);
+      ldb(rv.v, r + LEN * i);
       bool ok = !is_zero_n<N>(sv.v) && !geq_n<N>(sv.v, nmod) && !is_zero_n<N>(rv.v) && !geq_n<N>(rv.v, nmod);
       if (!ok) invalid_mask |= 1u << j;
       sc sm = S::cmov(S::to_mont(sv), S::one(), !ok);
@@ -172,14 +180,14 @@ struct SW {
       size_t i = tid + (size_t)j * T;
       bool ok = !((invalid_mask >> j) & 1);
       sc sv, rv, ev, pre;
-      load_be<N>(sv.v, s + LEN * i);
+      ldb(sv.v, s + LEN * i);
       sc sm = S::cmov(S::to_mont(sv), S::one(), !ok);
       for (int w = 0; w < N; w++) pre.v[w] = scratch[(size_t)w * cnt_items + i];
       sc sinv = S::mul(inv, pre);
       inv = S::mul(inv, sm);
       u32 flags = ok ? 0 : FL_INVALID;
-      load_be<N>(rv.v, r + LEN * i);
-      load_be<N>(ev.v, e + LEN * i);
+      ldb(rv.v, r + LEN * i);
+      ldb(ev.v, e + LEN * i);
       sc u1 = S::mul(ev, sinv);     // plain e * Montgomery s^-1 -> plain   (ec/index.js:206)
       sc u2 = S::mul(rv, sinv);     //                                        (ec/index.js:207)
       prep_store(i, cnt_items, u1.v, u2.v, flags, ws);
@@ -200,18 +208,33 @@ struct SW {
     ws[(size_t)(2 * N) * cnt_items + i] = flags;
   }
 
-  // Point.mul / mulAdd callers (short.js:422-441): k1, k2 any integers below 2^(32N), reduced mod n here
+  // k < 2^(8 LEN) -> k mod n.  One conditional subtraction when 2^(8 LEN) <= 2n; p521 (528-bit strings,
+  // 521-bit n) goes through the Montgomery round trip x -> xR -> x.
+  static EB_HD void reduce_scalar(u32* k) {
+    if (8 * C::LEN <= C::BITS) {
+      u32 nmod[N];
+      n_limbs(nmod);
+      if (geq_n<N>(k, nmod)) sub_n<N>(k, k, nmod);
+    } else {
+      typename S::fe t;
+      for (int w = 0; w < N; w++) t.v[w] = k[w];
+      t = S::from_mont(S::to_mont(t));
+      for (int w = 0; w < N; w++) k[w] = t.v[w];
+    }
+  }
+
+  // Point.mul / mulAdd callers (short.js:422-441): k1, k2 any integers below 2^(8 LEN), reduced mod n here
   // (for an on-curve point only the residue matters).  k1 == nullptr: no base-point term.
   static EB_HD void prep_scalars_item(size_t i, size_t cnt_items, const uint8_t* k1, const uint8_t* k2, u32* ws) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 nmod[N], u1[N], u2[N];
     n_limbs(nmod);
     u32 flags = 0;
     for (int w = 0; w < N; w++) u1[w] = 0;
-    if (k1) { load_be<N>(u1, k1 + LEN * i); if (geq_n<N>(u1, nmod)) sub_n<N>(u1, u1, nmod); }
+    if (k1) { ldb(u1, k1 + LEN * i); reduce_scalar(u1); }
     else flags |= FL_NOG;
-    load_be<N>(u2, k2 + LEN * i);
-    if (geq_n<N>(u2, nmod)) sub_n<N>(u2, u2, nmod);
+    ldb(u2, k2 + LEN * i);
+    reduce_scalar(u2);
     prep_store(i, cnt_items, u1, u2, flags, ws);
   }
 
@@ -272,24 +295,24 @@ struct SW {
   }
 
   static EB_HD aff load_point(const uint8_t* pts, size_t i) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     aff Q;
     fe t;
-    load_be<N>(t.v, pts + 2 * LEN * i);       Q.x = F::to_mont(t);
-    load_be<N>(t.v, pts + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
+    ldb(t.v, pts + 2 * LEN * i);       Q.x = F::to_mont(t);
+    ldb(t.v, pts + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
     return Q;
   }
   static EB_HD void store_point(uint8_t* out, size_t i, const aff& a) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     fe x = F::from_mont(a.x), y = F::from_mont(a.y);
-    store_be<N>(out + 2 * LEN * i, x.v);
-    store_be<N>(out + 2 * LEN * i + LEN, y.v);
+    stb(out + 2 * LEN * i, x.v);
+    stb(out + 2 * LEN * i + LEN, y.v);
   }
 
   // ---- main: one signature
   static EB_HD uint8_t verify_item(size_t i, size_t cnt_items, const uint8_t* pub, const uint8_t* r,
                                    const u32* ws, const u32* gtab, u32* qtab) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
     if (flags & FL_INVALID) return 0;   // ST_FALSE
     aff Q = load_point(pub, i);
@@ -299,7 +322,7 @@ struct SW {
     if (F::is_zero(acc.z)) return 0;
     fe z2 = F::sqr(acc.z);
     fe rp;
-    load_be<N>(rp.v, r + LEN * i);
+    ldb(rp.v, r + LEN * i);
     if (F::eq(acc.x, F::mul(F::to_mont(rp), z2))) return 1;
     u32 pmn[N]; C::p_minus_n(pmn);
     if (!geq_n<N>(rp.v, pmn)) {
@@ -315,7 +338,7 @@ struct SW {
   // short.js:516-526).  1 = point written, 7 = infinity, 4 = off-curve (replayed by SWReplay).
   static EB_HD uint8_t mul_add_item(size_t i, size_t cnt_items, const uint8_t* pts, const u32* ws, const u32* gtab,
                                     u32* qtab, uint8_t* out) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
     aff P = load_point(pts, i);
     if (!on_curve(P)) return 4;
@@ -328,11 +351,11 @@ struct SW {
 
   // G.mul(k) (short.js:422-427 -> _fixedNafMul, base.js:52-84): fixed table only
   static EB_HD uint8_t mul_g_item(size_t i, const uint8_t* k, const u32* gtab, uint8_t* out) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 nmod[N], kv[N];
     n_limbs(nmod);
-    load_be<N>(kv, k + LEN * i);
-    if (geq_n<N>(kv, nmod)) sub_n<N>(kv, kv, nmod);
+    ldb(kv, k + LEN * i);
+    reduce_scalar(kv);
     for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
     if (is_zero_n<N>(kv)) return 7;
     bool negg = (kv[0] & 1) == 0;

@@ -167,10 +167,10 @@ struct SWReplay {
   // Point.mul (k1 == nullptr) / G.mulAdd(k1, P, k2) for an off-curve P: the reference's schedule, then toP.
   static EB_HD uint8_t mul_add_item(size_t i, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, const u32* tab,
                                     uint8_t* out) {
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 u1[N], u2[N];
-    if (k1) load_be<N>(u1, k1 + LEN * i);
-    load_be<N>(u2, k2 + LEN * i);
+    if (k1) W::ldb(u1, k1 + LEN * i);
+    W::ldb(u2, k2 + LEN * i);
     aff P = W::load_point(pts, i);
     jac acc = k1 ? jmul_add(u1, u2, P, tab) : wnaf_mul(u2, P);
     for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
@@ -182,24 +182,24 @@ struct SWReplay {
   static EB_HD uint8_t verify_item(size_t i, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
                                    const u32* tab) {
     typedef typename S::fe sc;
-    const size_t LEN = 4 * N;
+    const size_t LEN = C::LEN;
     u32 nmod[N]; S::Params::mod(nmod);
     sc ev, rv, sv;
-    load_be<N>(ev.v, e + LEN * i); load_be<N>(rv.v, r + LEN * i); load_be<N>(sv.v, s + LEN * i);
+    W::ldb(ev.v, e + LEN * i); W::ldb(rv.v, r + LEN * i); W::ldb(sv.v, s + LEN * i);
     if (is_zero_n<N>(rv.v) || geq_n<N>(rv.v, nmod) || is_zero_n<N>(sv.v) || geq_n<N>(sv.v, nmod)) return 0;
     sc sinv = S::inv(S::to_mont(sv));
     sc u1 = S::mul(ev, sinv), u2 = S::mul(rv, sinv);
     aff Q;
     {
       fe t;
-      load_be<N>(t.v, pub + 2 * LEN * i);       Q.x = F::to_mont(t);
-      load_be<N>(t.v, pub + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
+      W::ldb(t.v, pub + 2 * LEN * i);       Q.x = F::to_mont(t);
+      W::ldb(t.v, pub + 2 * LEN * i + LEN); Q.y = F::to_mont(t);
     }
     jac acc = jmul_add(u1.v, u2.v, Q, tab);
     if (F::is_zero(acc.z)) return 0;
     fe z2 = F::sqr(acc.z);
     fe rp;
-    load_be<N>(rp.v, r + LEN * i);
+    W::ldb(rp.v, r + LEN * i);
     if (F::eq(acc.x, F::mul(F::to_mont(rp), z2))) return 1;
     u32 pmn[N]; C::p_minus_n(pmn);
     if (!geq_n<N>(rp.v, pmn)) {

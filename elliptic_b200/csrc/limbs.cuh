@@ -219,6 +219,18 @@ EB_HD void store_be(uint8_t* p, const u32* a) {
     q[2] = (uint8_t)(a[i] >> 8);  q[3] = (uint8_t)a[i];
   }
 }
+
+// Big-endian byte strings whose length is not a multiple of 4 (p521: 66 bytes in 18 limbs).
+template <int N>
+EB_HD void load_be_len(u32* r, const uint8_t* p, int len) {
+  for (int w = 0; w < N; w++) r[w] = 0;
+  for (int k = 0; k < len; k++) r[k >> 2] |= (u32)p[len - 1 - k] << (8 * (k & 3));
+}
+template <int N>
+EB_HD void store_be_len(uint8_t* p, const u32* a, int len) {
+  for (int k = 0; k < len; k++) p[len - 1 - k] = (uint8_t)(a[k >> 2] >> (8 * (k & 3)));
+}
+
 template <int N>
 EB_HD void load_le(u32* r, const uint8_t* p) {
 #pragma unroll

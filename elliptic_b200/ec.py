@@ -27,6 +27,9 @@ _CURVES = {
     "p384": dict(id=nat.CURVE_P384, len=48,
                  n=0xffffffffffffffffffffffffffffffffffffffffffffffffc7634d81f4372ddf581a0db248b0a77aecec196accc52973,
                  p=2**384 - 2**128 - 2**96 + 2**32 - 1),
+    "p521": dict(id=nat.CURVE_P521, len=66,
+                 n=0x1fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
+                 p=2**521 - 1),
 }
 
 
@@ -368,7 +371,7 @@ class EC:
         return out
 
     def _mul_common(self, k1, k2, pts):
-        if self.name not in ("secp256k1", "p256", "p384"):
+        if self.name not in ("secp256k1", "p256", "p384", "p521"):
             raise EllipticError("mul/mulAdd batches: short curves only")
         lib = nat.init(self._device)
         n, ln = len(k2), self._len

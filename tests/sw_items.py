@@ -2,7 +2,7 @@
 import random
 
 
-def sw_edge_items(ec, ln, seed=5, count=60):
+def sw_edge_items(ec, ln, seed=5, count=60, ebits=None):
     """(e, r, s, x, y) tuples covering ec/index.js:188-229 for a non-GLV curve."""
     n, G, P = ec.n, ec.g, ec.curve.p
     rnd = random.Random(seed)
@@ -11,8 +11,8 @@ def sw_edge_items(ec, ln, seed=5, count=60):
     items = []
     for t in range(count):
         d, Q = keys[t % 4], pubs[t % 4]
-        e = rnd.randrange(2 ** (8 * ln))
-        sig = ec.sign(e.to_bytes(ln, "big"), d)
+        e = rnd.randrange(2 ** (ebits or 8 * ln))
+        sig = ec.sign(e, d)          # BN form: _truncateToN measures the value, not a padded array
         r, s = sig.r, sig.s
         k = t % 10
         if k == 1: e ^= 1 << rnd.randrange(8 * ln)
@@ -24,17 +24,21 @@ def sw_edge_items(ec, ln, seed=5, count=60):
         if k == 7: s ^= 1 << rnd.randrange(8 * ln - 1)
         items.append((e, r, s, Q.x, Q.y))
     d, Q = keys[0], pubs[0]
-    r, s = rnd.randrange(1, n), rnd.randrange(1, n)
-    items.append(((-r * d) % n, r, s, Q.x, Q.y))       # R = O
-    items.append(((r * d) % n, r, s, Q.x, Q.y))        # u1*G == u2*Q
+    lim = 2 ** (ebits or 8 * ln)          # messages must not be shortened by _truncateToN (p521: below 2^520)
+    for sign in (-1, 1):                  # e = -r d: R = O;  e = r d: u1*G == u2*Q
+        while True:
+            r, s = rnd.randrange(1, n), rnd.randrange(1, n)
+            if (sign * r * d) % n < lim:
+                break
+        items.append(((sign * r * d) % n, r, s, Q.x, Q.y))
     items.append((5, r, s, Q.x, (Q.y + 1) % P))        # off-curve -> NEEDS_HOST
-    sig = ec.sign((7).to_bytes(ln, "big"), 1); items.append((7, sig.r, sig.s, G.x, G.y))      # Q = G
-    mg = G.neg(); sig = ec.sign((8).to_bytes(ln, "big"), n - 1); items.append((8, sig.r, sig.s, mg.x, mg.y))
-    sig = ec.sign(b"\x00" * ln, d); items.append((0, sig.r, sig.s, Q.x, Q.y))                 # e = 0
+    sig = ec.sign(7, 1); items.append((7, sig.r, sig.s, G.x, G.y))      # Q = G
+    mg = G.neg(); sig = ec.sign(8, n - 1); items.append((8, sig.r, sig.s, mg.x, mg.y))
+    sig = ec.sign(0, d); items.append((0, sig.r, sig.s, Q.x, Q.y))                 # e = 0
     return items
 
 
-def sw_off_curve_items(ec, ln, seed=4, count=12):
+def sw_off_curve_items(ec, ln, seed=4, count=12, ebits=None):
     """Un-validated off-curve keys (ec/key.js:95).  Even items are minted so that the reference's own
     schedule lands on x(R) == r (verdict TRUE); odd items are random (FALSE)."""
     n, P = ec.n, ec.curve.p
@@ -46,8 +50,9 @@ def sw_off_curve_items(ec, ln, seed=4, count=12):
         Q = ec.curve.point(x, y)
         if ec.curve.validate(Q):
             continue
+        lim = 2 ** (ebits or 8 * ln)
         if len(items) % 2:
-            items.append((rnd.randrange(n), rnd.randrange(1, n), rnd.randrange(1, n), x, y))
+            items.append((rnd.randrange(min(n, lim)), rnd.randrange(1, n), rnd.randrange(1, n), x, y))
             continue
         u1, u2 = rnd.randrange(1, n), rnd.randrange(1, n)
         R = ec.g.jmul_add(u1, Q, u2)
@@ -59,6 +64,8 @@ def sw_off_curve_items(ec, ln, seed=4, count=12):
             continue
         s = r * pow(u2, -1, n) % n
         e = u1 * s % n
+        if e >= lim:
+            continue
         # u1, u2 recomputed by verify are the same residues, so the schedule and hence R repeat
         items.append((e, r, s, x, y))
     return items
@@ -73,4 +80,4 @@ def sw_expected(ec, ln, it, replay=True):
         return 0
     if not replay and not ec.curve.validate(ec.curve.point(x, y)):
         return 4
-    return int(ec.verify((e if e < n else e - n).to_bytes(ln, "big"), {"r": r, "s": s}, {"x": x, "y": y}))
+    return int(ec.verify(e if e < n else e - n, {"r": r, "s": s}, {"x": x, "y": y}))

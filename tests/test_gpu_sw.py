@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 KATS = json.load(open(os.path.join(G, "ecdsa_kats.json")))
-CURVES = {"p256": (2, 32), "p384": (3, 48)}
+CURVES = {"p256": (2, 32), "p384": (3, 48), "p521": (6, 66)}
+NL = {"p256": 8, "p384": 12, "p521": 18}          # 32-bit limbs per field element (p521: 17 + one spare)
 
 
 def limbs(vals, n):
@@ -27,13 +28,13 @@ def ints(a):
     return [sum(int(a[i, k]) << (32 * k) for k in range(a.shape[1])) for i in range(a.shape[0])]
 
 
-@pytest.mark.parametrize("name", ["p256", "p384"])
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
 def test_montgomery_field_bit_exact(native, name):
     from elliptic_b200 import _native as nat
     from oracle.ref_py import curves
     cid, ln = CURVES[name]
     p = curves.get(name).curve.p
-    nl = ln // 4
+    nl = NL[name]
     rnd = random.Random(3)
     edge = [0, 1, 2, p - 1, p - 2, (1 << (8 * ln)) - 1, p, p + 1, 1 << (8 * ln - 1), (1 << 32) - 1, 1 << 32]
     a = edge + [rnd.randrange(1 << (8 * ln)) for _ in range(1500)]
@@ -53,20 +54,20 @@ def test_montgomery_field_bit_exact(native, name):
         assert g == pow(x % p, p - 2, p)
 
 
-@pytest.mark.parametrize("name", ["p256", "p384"])
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
 def test_fixed_base_table(native, name):
     from elliptic_b200 import _native as nat
     from oracle.ref_py.ec import EC
     cid, ln = CURVES[name]
     ec = EC(name)
-    p, n, nl = ec.curve.p, ec.n, ln // 4
+    p, n, nl = ec.curve.p, ec.n, NL[name]
     W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     nat.check(native.eb200_selftest_gtab_dims(cid, ctypes.byref(W), ctypes.byref(E), ctypes.byref(B)))
     W, E, B = W.value, E.value, B.value
     tab = np.zeros(W * E * 2 * nl, np.uint32)
     nat.check(native.eb200_selftest_gtab(cid, tab.ctypes.data, tab.size))
     tab = tab.reshape(W, E, 2, nl)
-    R = 1 << (8 * ln)
+    R = 1 << (32 * nl)
     rnd = random.Random(6)
     for j, i in [(0, 0), (0, E - 1), (W - 1, 0), (W - 1, E - 1)] + [(rnd.randrange(W), rnd.randrange(E)) for _ in range(30)]:
         pt = ec.g.mul(((2 * i + 1) << (B * j)) % n)
@@ -74,14 +75,14 @@ def test_fixed_base_table(native, name):
         assert (x, y) == (pt.x * R % p, pt.y * R % p), (name, j, i)     # Montgomery form
 
 
-@pytest.mark.parametrize("name", ["p256", "p384"])
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
 def test_verify_parity(native, name):
     from elliptic_b200.ec import EC as GpuEC
     from oracle.ref_py.ec import EC
     from sw_items import sw_edge_items, sw_expected
     cid, ln = CURVES[name]
     ec = EC(name)
-    items = sw_edge_items(ec, ln, seed=11, count=200)
+    items = sw_edge_items(ec, ln, seed=11, count=200 if ln < 66 else 40, ebits=520 if ln == 66 else None)
     pack = lambda k: np.frombuffer(b"".join(it[k].to_bytes(ln, "big") for it in items), np.uint8).reshape(-1, ln)
     st = GpuEC(name).verify_batch_packed(pack(0), pack(1), pack(2), np.concatenate([pack(3), pack(4)], axis=1))
     exp = [sw_expected(ec, ln, it) for it in items]
@@ -90,7 +91,7 @@ def test_verify_parity(native, name):
     assert {0, 1} <= set(exp)
 
 
-@pytest.mark.parametrize("name", ["p256", "p384"])
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
 def test_off_curve_keys_get_the_reference_answer(native, name):
     """Un-validated off-curve keys (ec/key.js:95) are re-run by the exact-replay kernel
     (ecdsa_sw_replay.cuh); no item may come back as NEEDS_HOST."""
@@ -99,10 +100,10 @@ def test_off_curve_keys_get_the_reference_answer(native, name):
     from sw_items import sw_off_curve_items
     cid, ln = CURVES[name]
     ec = EC(name)
-    items = sw_off_curve_items(ec, ln, seed=8, count=40)
+    items = sw_off_curve_items(ec, ln, seed=8, count=40 if ln < 66 else 12, ebits=520 if ln == 66 else None)
     pack = lambda k: np.frombuffer(b"".join(it[k].to_bytes(ln, "big") for it in items), np.uint8).reshape(-1, ln)
     st = GpuEC(name).verify_batch_packed(pack(0), pack(1), pack(2), np.concatenate([pack(3), pack(4)], axis=1))
-    exp = [int(ec.verify(it[0].to_bytes(ln, "big"), {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
+    exp = [int(ec.verify(it[0], {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
     assert [int(v) for v in st] == exp
     assert exp.count(1) == len(items) // 2
 
@@ -115,12 +116,12 @@ def test_reference_maxwell_vectors_on_gpu(native):
 
 
 def test_reference_rfc6979_vectors_verify_on_gpu(native):
-    """test/ecdsa-test.js:135-350 (p256, p384): the published (r, s) must verify."""
+    """test/ecdsa-test.js:135-350 (p256, p384, p521): the published (r, s) must verify."""
     from elliptic_b200.ec import EC as GpuEC
     hs = {"sha1": hashlib.sha1, "sha224": hashlib.sha224, "sha256": hashlib.sha256, "sha384": hashlib.sha384, "sha512": hashlib.sha512}
     seen = 0
     for blk in KATS["rfc6979"]:
-        if blk["curve"] not in ("p256", "p384"):
+        if blk["curve"] not in ("p256", "p384", "p521"):
             continue
         gec = GpuEC(blk["curve"])
         for c in blk["cases"]:
@@ -129,7 +130,7 @@ def test_reference_rfc6979_vectors_verify_on_gpu(native):
             bad = bytearray(dg); bad[0] ^= 1
             assert gec.verify(bytes(bad), {"r": c["r"], "s": c["s"]}, {"x": blk["x"], "y": blk["y"]}) is False
             seen += 1
-    assert seen >= 6
+    assert seen >= 9
 
 
 @pytest.mark.parametrize("name", ["secp256k1", "p256", "p384"])
@@ -180,7 +181,7 @@ def test_sec1_key_formats_on_gpu(native, name):
     assert {1, 0, 2, 6} <= set(exp_c) and {1, 5, 6} <= set(exp_u)
 
 
-@pytest.mark.parametrize("name", ["p256", "p384"])
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
 def test_mul_and_mul_add_batches(native, name):
     """curve.point(x, y).mul(k) (_wnafMul), G.mul(k), G.mulAdd(k1, P, k2) (short.js:422-441) on the non-GLV
     curves: hostemu edge cases (oversize / zero scalars, P = +-G, off-curve points) plus random items."""
@@ -206,7 +207,7 @@ def test_mul_and_mul_add_batches(native, name):
     assert g.g_mul_batch([c[1] for c in cases]) == [ref(ec.g.mul(c[1])) for c in cases]
 
 
-@pytest.mark.parametrize("name", ["secp256k1", "p256", "p384"])
+@pytest.mark.parametrize("name", ["secp256k1", "p256", "p384", "p521"])
 def test_ecdh_derive_on_short_curves(native, name):
     """KeyPair.derive (ec/key.js:102-107; test/ecdh-test.js:8-43): shared x equals the oracle's, both
     sides agree, and the twist-attack point {x: 14, y: 16} is refused with the reference's message."""

@@ -80,12 +80,12 @@ def test_verify_pipeline_against_oracle(he):
     assert [int(v) for v in st] == [_expected(ec, it) for it in items]
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
 def test_sw_verify_pipeline_against_oracle(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     from sw_items import sw_edge_items, sw_expected
     ec = EC(name)
-    items = sw_edge_items(ec, ln, seed=21, count=30)
+    items = sw_edge_items(ec, ln, seed=21, count=30 if ln < 66 else 12, ebits=520 if ln == 66 else None)
     n = len(items)
     col = lambda k: b"".join(it[k].to_bytes(ln, "big") for it in items)
     pub = b"".join(it[3].to_bytes(ln, "big") + it[4].to_bytes(ln, "big") for it in items)
@@ -194,13 +194,13 @@ def test_sign_and_hash_bodies_against_oracle(he):
         assert bytes(o) == hashlib.sha256(msg).digest()
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
 def test_sw_replay_matches_reference_schedule_point_for_point(he, name, cid, ln):
     """The off-curve replay (ecdsa_sw_replay.cuh) must land on the same Jacobian triple as the
     oracle's _wnaf_mul_add, not just the same verdict: the coordinates are compared exactly."""
     from oracle.ref_py.ec import EC
     ec = EC(name)
-    n, p, k = ec.n, ec.curve.p, ln // 4
+    n, p, k = ec.n, ec.curve.p, {32: 8, 48: 12, 66: 18}[ln]
     rnd = random.Random(9 + cid)
     cases = []
     for t in range(10):
@@ -226,18 +226,18 @@ def test_sw_replay_matches_reference_schedule_point_for_point(he, name, cid, ln)
             assert got == (ref.x % p, ref.y % p, ref.z % p), (u1, u2, x, y)
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
 def test_sw_replay_verdicts_for_off_curve_keys(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     from sw_items import sw_off_curve_items
     ec = EC(name)
-    items = sw_off_curve_items(ec, ln, seed=4, count=12)
+    items = sw_off_curve_items(ec, ln, seed=4, count=12 if ln < 66 else 6, ebits=520 if ln == 66 else None)
     n = len(items)
     col = lambda k: b"".join(it[k].to_bytes(ln, "big") for it in items)
     pub = b"".join(it[3].to_bytes(ln, "big") + it[4].to_bytes(ln, "big") for it in items)
     st = (ctypes.c_uint8 * n)()
     he.he_sw_replay_verify(cid, ctypes.c_size_t(n), col(0), col(1), col(2), pub, st)
-    exp = [int(ec.verify(it[0].to_bytes(ln, "big"), {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
+    exp = [int(ec.verify(it[0], {"r": it[1], "s": it[2]}, {"x": it[3], "y": it[4]})) for it in items]
     assert [int(v) for v in st] == exp
     assert 1 in exp and 0 in exp
 
@@ -265,7 +265,7 @@ def mul_cases(ec, seed=3, bits=256):
     return cases
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
 def test_sw_mul_and_mul_add_bodies_against_oracle(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     ec = EC(name)
