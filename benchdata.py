@@ -48,6 +48,10 @@ CURVES = {
              0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973, -3,
              0xAA87CA22BE8B05378EB1C71EF320AD746E1D3B628BA79B9859F741E082542A385502F25DBF55296C3A545E3872760AB7,
              0x3617DE4A96262C6F5D9E98BF9292DC29F8F41DBD289A147CE9DA3113B5F0B8C00A60B1CE1D7E819D7A431D7C90EA0E5F, 48),
+    "p521": (2**521 - 1,
+             0x1FFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFA51868783BF2F966B7FCC0148F709A5D03BB5C9B8899C47AEBB6FB71E91386409, -3,
+             0xC6858E06B70404E9CD9E3ECB662395B4429C648139053FB521F828AF606B4D3DBAA14B5E77EFE75928FE1DC127A2FFA8DE3348B3C1856A429BF97E7E31C2E5BD66,
+             0x11839296A789A3BC0045C8A5FB42C7D1BD998F54449579B446817AFBD17273E662C97EE72995EF42640C550B9013FAD0761353C7086A272C24088BE94769FD16650, 66),
 }
 
 
@@ -116,7 +120,9 @@ def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every
             if i >= n_items:
                 continue
             e = _stream(seed, b"msg", i)
-            if LEN > 32:
+            if LEN > 64:       # p521: a 512-bit digest (longer values would be shortened by _truncateToN)
+                e = (e << 256) | _stream(seed, b"msg2", i)
+            elif LEN > 32:
                 e = (e << (8 * (LEN - 32))) | (_stream(seed, b"msg2", i) >> (8 * (64 - LEN)))
             r = R[j][0] % N
             s = kinv[j] * (e + r * d[j]) % N

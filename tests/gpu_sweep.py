@@ -19,8 +19,8 @@ CACHE = "/tmp/eb200_cache"
 res = {}
 for name in which:
     t = time.time()
-    if name in ("secp256k1", "p256", "p384"):
-        seed = {"secp256k1": 0xE1110002, "p256": 0xE1110256, "p384": 0xE1110384}[name]
+    if name in ("secp256k1", "p256", "p384", "p521"):
+        seed = {"secp256k1": 0xE1110002, "p256": 0xE1110256, "p384": 0xE1110384, "p521": 0xE1110521}[name]
         ds = benchdata.gen_ecdsa_verify(name, n, seed=seed, cache_dir=CACHE)
         ec = EC(name)
         run = lambda: ec.verify_batch_packed(ds["e"], ds["r"], ds["s"], ds["pub"])
