@@ -159,7 +159,11 @@ EB_HD fe fe_sqr_inl(const fe& a) {
 #endif
 #if defined(__CUDACC__) && EB_FE_OUTLINE
 __host__ __device__ __noinline__ fe fe_mul(fe a, fe b) { return fe_mul_inl(a, b); }
+#if defined(EB_FE_SQR_INLINE) && EB_FE_SQR_INLINE          // experiment: squarer inlined, multiplier out of line
+EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
+#else
 __host__ __device__ __noinline__ fe fe_sqr(fe a) { return fe_sqr_inl(a); }
+#endif
 #else
 EB_HD fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
 EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
@@ -176,7 +180,7 @@ EB_D fe fe_add_ptx(const fe& a, const fe& b) {
 #pragma unroll
   for (int i = 1; i < 8; i++) EB_ADDC_CC(r.v[i], a.v[i], b.v[i]);
   EB_ADDC(cy, Z, Z);
-  u32 kK = cy * K256_C0;
+  u32 kK = (0u - cy) & K256_C0;          // mask, not a multiply: IMAD would take the multiplier pipe
   EB_ADD_CC(r.v[0], r.v[0], kK);
   EB_ADDC_CC(r.v[1], r.v[1], cy);
   EB_ADDC(c2, Z, Z);
@@ -200,8 +204,8 @@ EB_D fe fe_sub_ptx(const fe& a, const fe& b) {
 #pragma unroll
   for (int i = 1; i < 8; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
   asm volatile("subc.u32 %0, %1, %1;" : "=r"(bw) : "r"(Z));      // 0 or 0xFFFFFFFF
+  u32 kK = bw & K256_C0;
   bw &= 1;
-  u32 kK = bw * K256_C0;
   asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(kK));
   asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(r.v[1]) : "r"(bw));
   asm volatile("subc.u32 %0, %1, %1;" : "=r"(b2) : "r"(Z));

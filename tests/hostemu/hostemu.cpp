@@ -311,3 +311,15 @@ extern "C" void he_drbg_first_k(const uint8_t* priv, const uint8_t* msg, uint8_t
 extern "C" int he_der_import(const uint8_t* data, size_t n, size_t len, uint8_t* r, uint8_t* s) {
   return der_import(data, n, len, r, s) ? 1 : 0;
 }
+
+// ---------------------------------------------------------------------------
+// verify with the accumulator in "shared memory" (ecdsa_k256_smem.cuh), stride 1 on the host
+#include "../../elliptic_b200/csrc/ecdsa_k256_smem.cuh"
+extern "C" void he_verify_sm(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
+                             const u32* gtab, uint8_t* status) {
+  std::vector<u32> ws((size_t)PREP_WORDS * N), scratch((size_t)8 * N), qtab((size_t)QTAB_WORDS * N);
+  size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
+  for (size_t t = 0; t < T; t++) prep_thread(t, T, N, e, r, s, ws.data(), scratch.data());
+  u32 acc[SM_WORDS];
+  for (size_t i = 0; i < N; i++) status[i] = verify_item_sm<1>(i, N, pub, r, ws.data(), gtab, qtab.data(), acc);
+}

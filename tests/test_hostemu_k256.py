@@ -78,6 +78,10 @@ def test_verify_pipeline_against_oracle(he):
     st = (ctypes.c_uint8 * n)()
     he.he_verify(ctypes.c_size_t(n), col(0), col(1), col(2), pub, gtab.ctypes.data_as(ctypes.c_void_p), st)
     assert [int(v) for v in st] == [_expected(ec, it) for it in items]
+    # the shared-memory-accumulator variant of the same core must agree item by item
+    st2 = (ctypes.c_uint8 * n)()
+    he.he_verify_sm(ctypes.c_size_t(n), col(0), col(1), col(2), pub, gtab.ctypes.data_as(ctypes.c_void_p), st2)
+    assert list(st2) == list(st)
 
 
 @pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
