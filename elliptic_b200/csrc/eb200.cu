@@ -14,6 +14,7 @@
 #include "ecdsa_k256_sign_fast.cuh"
 #include "der_sig.cuh"
 #include "ecdsa_k256_smem.cuh"
+#include "ecdsa_sw_sign.cuh"
 #include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
@@ -257,6 +258,33 @@ sw_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restr
   if (i >= N || status[i] != ST_NEEDS_HOST) return;
   status[i] = SWReplay<C>::verify_item(i, e, r, s, pub, tab);
 }
+// EC.sign on p256 / p384 (ecdsa_sw_sign.cuh)
+template <class SG>
+__global__ void __launch_bounds__(128)
+sw_sign_nonce_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv,
+                     const u32* __restrict__ gtab, u32* __restrict__ ws, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) SG::nonce_item(i, N, e, priv, gtab, ws, status);
+}
+template <class SG>
+__global__ void __launch_bounds__(128)
+sw_sign_finish_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
+                      const u32* __restrict__ ws, u32* __restrict__ scratch, uint8_t* __restrict__ r,
+                      uint8_t* __restrict__ s, uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = (size_t)gridDim.x * blockDim.x;
+  SG::finish_thread(tid, T, N, e, priv, canonical, ws, scratch, r, s, recid, status);
+}
+template <class SG>
+__global__ void __launch_bounds__(128)
+sw_sign_slow_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ priv, u32 canonical,
+                    const u32* __restrict__ gtab, uint8_t* __restrict__ r, uint8_t* __restrict__ s,
+                    uint8_t* __restrict__ recid, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || status[i] != ST_NEEDS_HOST) return;
+  status[i] = SG::slow_item(i, e, priv, canonical, gtab, r, s, recid);
+}
+
 // Point.mul / mulAdd batches on the non-GLV short curves
 template <class C>
 __global__ void __launch_bounds__(128)
@@ -979,39 +1007,64 @@ int eb200_mul_add_batch(int curve, size_t n, const uint8_t* k1, const uint8_t* k
 }
 
 // ---- ECDSA sign (secp256k1, RFC 6979 nonces on the GPU) -------------------------------------------------
+}  // extern "C"
+
+template <class SG>
+static int sw_sign_launch(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_k, u32 canonical, u32* d_sws, u32* d_scr,
+                          uint8_t* d_r, uint8_t* d_s, uint8_t* d_id, cudaStream_t st) {
+  unsigned nb = (unsigned)((n + 127) / 128);
+  size_t T = (n + SG::BATCH - 1) / SG::BATCH;
+  sw_sign_nonce_kernel<SG><<<nb, 128, 0, st>>>(n, d_e, d_k, g.gtab[curve], d_sws, g.d_status);
+  CK(cudaGetLastError());
+  sw_sign_finish_kernel<SG><<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, g.d_status);
+  CK(cudaGetLastError());
+  sw_sign_slow_kernel<SG><<<nb, 128, 0, st>>>(n, d_e, d_k, canonical, g.gtab[curve], d_r, d_s, d_id, g.d_status);
+  CK(cudaGetLastError());
+  return EB200_OK;
+}
+
+extern "C" {
+
 int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,
                            uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (curve != EB200_CURVE_SECP256K1 && curve != EB200_CURVE_P256 && curve != EB200_CURVE_P384) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   if (!e || !priv || !out_r || !out_s || !out_recid || !status) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
   int rc = ensure_table(curve);
   if (rc) return rc;
-  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (4 * 32 + 1) + 256))) return rc;
+  const size_t len = curve_len(curve), limbs = len / 4;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (4 * len + 1) + 256))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
-  const size_t ws_bytes = align256((size_t)SIGN_WS_WORDS * 4 * n);
-  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_bytes + (size_t)SIGN_SCRATCH_WORDS * 4 * n))) return rc;
-  uint8_t *d_e = g.d_in, *d_k = d_e + 32 * n, *d_r = d_k + 32 * n, *d_s = d_r + 32 * n, *d_id = d_s + 32 * n;
+  const size_t ws_bytes = align256(4 * limbs * 4 * n);                 // X, Y, Z, k
+  if ((rc = grow(&g.d_ws, &g.d_ws_cap, ws_bytes + 2 * limbs * 4 * n))) return rc;
+  uint8_t *d_e = g.d_in, *d_k = d_e + len * n, *d_r = d_k + len * n, *d_s = d_r + len * n, *d_id = d_s + len * n;
   u32 *d_sws = (u32*)g.d_ws, *d_scr = (u32*)(g.d_ws + ws_bytes);
   const u32 canonical = flags & EB200_SIGN_CANONICAL;
   cudaStream_t st = g.stream;
   CK(cudaEventRecord(g.ev[0], st));
-  CK(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_k, priv, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_e, e, len * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_k, priv, len * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
-  unsigned nb = (unsigned)((n + 127) / 128);
-  size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
-  k256_sign_nonce_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, g.gtab[curve], d_sws, g.d_status);
-  CK(cudaGetLastError());
-  k256_sign_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, g.d_status);
-  CK(cudaGetLastError());
-  k256_sign_slow_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, canonical, g.gtab[curve], d_r, d_s, d_id, g.d_status);
-  CK(cudaGetLastError());
+  if (curve == EB200_CURVE_P256) {
+    if ((rc = sw_sign_launch<SWSign<P256, Sha256W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
+  } else if (curve == EB200_CURVE_P384) {
+    if ((rc = sw_sign_launch<SWSign<P384, Sha384W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
+  } else {
+    unsigned nb = (unsigned)((n + 127) / 128);
+    size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
+    k256_sign_nonce_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, g.gtab[curve], d_sws, g.d_status);
+    CK(cudaGetLastError());
+    k256_sign_finish_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, g.d_status);
+    CK(cudaGetLastError());
+    k256_sign_slow_kernel<<<nb, 128, 0, st>>>(n, d_e, d_k, canonical, g.gtab[curve], d_r, d_s, d_id, g.d_status);
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(out_r, d_r, 32 * n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(out_s, d_s, 32 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_r, d_r, len * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_s, d_s, len * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(out_recid, d_id, n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(g.ev[3], st));

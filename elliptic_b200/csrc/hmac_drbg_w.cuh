@@ -1,0 +1,189 @@
+// hmac_drbg_w.cuh -- HmacDRBG (hmac-drbg 1.0.1, dist/elliptic.js:8686-8800) over SHA-256 or SHA-384, word-oriented
+// and entirely in registers, for the one shape EC.prototype.sign uses it in (lib/elliptic/ec/index.js:135-160):
+// entropy = the private key, nonce = the truncated message, both exactly one digest long (32 bytes with SHA-256
+// on a 256-bit curve, 48 bytes with SHA-384 on p384), no personalisation string, generate(digest length).
+//
+// HMAC pad states are computed once per key and reused by the calls that share it; every message fed to the
+// hash is built directly as big-endian words (the seed material sits one byte off the word grid behind the
+// 0x00 / 0x01 separator, hence the funnel shifts).
+#pragma once
+#include "sha2.cuh"
+
+namespace eb {
+
+struct Sha256W {
+  typedef u32 W;
+  static constexpr int D = 8;              // digest words
+  static constexpr int WB = 32;            // bits per word
+  static EB_HD void iv(W* s) {
+    const W v[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (int i = 0; i < 8; i++) s[i] = v[i];
+  }
+  static EB_HD void compress(W* st, const W* win) {
+    W w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = win[i];
+    W a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+      W wi;
+      if (i < 16) wi = w[i];
+      else {
+        W w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+        W s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+        W s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+        wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        w[i & 15] = wi;
+      }
+      W S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+      W ch = (e & f) ^ (~e & g);
+      W t1 = h + S1 + ch + sha256_k(i) + wi;
+      W S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+      W mj = (a & b) ^ (a & c) ^ (b & c);
+      h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+  }
+};
+
+struct Sha384W {
+  typedef u64 W;
+  static constexpr int D = 6;
+  static constexpr int WB = 64;
+  static EB_HD void iv(W* s) {
+    const W v[8] = {0xcbbb9d5dc1059ed8ULL, 0x629a292a367cd507ULL, 0x9159015a3070dd17ULL, 0x152fecd8f70e5939ULL,
+                    0x67332667ffc00b31ULL, 0x8eb44a8768581511ULL, 0xdb0c2e0d64f98fa7ULL, 0x47b5481dbefa4fa4ULL};
+    for (int i = 0; i < 8; i++) s[i] = v[i];
+  }
+  static EB_HD void compress(W* st, const W* win) {
+    W w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = win[i];
+    W a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll 8
+    for (int i = 0; i < 80; i++) {
+      W wi;
+      if (i < 16) wi = w[i];
+      else {
+        W w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+        W s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+        W s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+        wi = w[i & 15] + s0 + w[(i + 9) & 15] + s1;
+        w[i & 15] = wi;
+      }
+      W S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
+      W ch = (e & f) ^ (~e & g);
+      W t1 = h + S1 + ch + sha512_k(i) + wi;
+      W S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
+      W mj = (a & b) ^ (a & c) ^ (b & c);
+      h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + S0 + mj;
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+  }
+};
+
+template <class H>
+struct HmacDrbgW {
+  typedef typename H::W W;
+  static constexpr int D = H::D;
+  static constexpr int WB = H::WB;
+  static constexpr int DBYTES = D * WB / 8;          // digest = key = V length in bytes
+  static constexpr int BBYTES = 16 * WB / 8;         // block length in bytes
+  W kin[8], kout[8];                                  // hash states after the ipad / opad block of the current K
+  W V[D];
+  bool first;
+
+  EB_HD void set_key(const W* key) {
+    W w[16];
+    const W ipad = (W)0x3636363636363636ULL, opad = (W)0x5c5c5c5c5c5c5c5cULL;
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = (i < D ? key[i] : (W)0) ^ ipad;
+    H::iv(kin);
+    H::compress(kin, w);
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = (i < D ? key[i] : (W)0) ^ opad;
+    H::iv(kout);
+    H::compress(kout, w);
+  }
+  // finishes an HMAC: `inner` is the inner hash state after all message blocks
+  EB_HD void outer(const W* inner, W* out) const {
+    W w[16], st[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) w[i] = inner[i];
+    w[D] = (W)0x80 << (WB - 8);
+    w[15] = (W)((BBYTES + DBYTES) * 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = kout[i];
+    H::compress(st, w);
+#pragma unroll
+    for (int i = 0; i < D; i++) out[i] = st[i];
+  }
+  // HMAC(K, V) and HMAC(K, V || sep): one inner message block
+  EB_HD void mac_v(W* out, bool with_sep, W sep) const {
+    W w[16], st[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) w[i] = V[i];
+    if (with_sep) w[D] = (sep << (WB - 8)) | ((W)0x80 << (WB - 16));
+    else w[D] = (W)0x80 << (WB - 8);
+    w[15] = (W)((BBYTES + DBYTES + (with_sep ? 1 : 0)) * 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = kin[i];
+    H::compress(st, w);
+    outer(st, out);
+  }
+  // HMAC(K, V || sep || a || b), a and b one digest long each: 3 D + 1 words in two blocks
+  EB_HD void mac_v_sep_seed(W sep, const W* a, const W* b, W* out) const {
+    W m[32], st[8];
+#pragma unroll
+    for (int i = 0; i < 32; i++) m[i] = 0;
+#pragma unroll
+    for (int i = 0; i < D; i++) m[i] = V[i];
+    m[D] = (sep << (WB - 8)) | (a[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < D; i++) m[D + i] = (a[i - 1] << (WB - 8)) | (a[i] >> 8);
+    m[2 * D] = (a[D - 1] << (WB - 8)) | (b[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < D; i++) m[2 * D + i] = (b[i - 1] << (WB - 8)) | (b[i] >> 8);
+    m[3 * D] = (b[D - 1] << (WB - 8)) | ((W)0x80 << (WB - 16));
+    m[31] = (W)((BBYTES + 3 * DBYTES + 1) * 8);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = kin[i];
+    H::compress(st, m);
+    H::compress(st, m + 16);
+    outer(st, out);
+  }
+
+  // new HmacDRBG({hash, entropy: priv, nonce: msg})   (dist:8692-8733)
+  EB_HD void init(const W* priv, const W* msg) {
+    W K[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) { K[i] = 0; V[i] = (W)0x0101010101010101ULL; }
+    set_key(K);
+    mac_v_sep_seed(0x00, priv, msg, K);
+    set_key(K);
+    mac_v(V, false, 0);
+    mac_v_sep_seed(0x01, priv, msg, K);
+    set_key(K);
+    mac_v(V, false, 0);
+    first = true;
+  }
+  // generate(digest length)   (dist:8771-8797); the trailing _update() is deferred to the next call
+  EB_HD void generate(W* out) {
+    if (!first) {
+      W K[D];
+      mac_v(K, true, 0x00);
+      set_key(K);
+      mac_v(V, false, 0);
+    }
+    first = false;
+    mac_v(V, false, 0);
+#pragma unroll
+    for (int i = 0; i < D; i++) out[i] = V[i];
+  }
+};
+
+}  // namespace eb

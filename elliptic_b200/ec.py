@@ -290,18 +290,20 @@ class EC:
     def sign_batch(self, msgs, privs, canonical=False, msg_bit_length=None):
         """Batch of EC.prototype.sign (ec/index.js:110-186) with the default hash and RFC 6979 nonces
         (no `pers`, no custom `k`).  Returns (r list, s list, recoveryParam array)."""
-        if self.name != "secp256k1":
-            raise EllipticError("sign_batch: only secp256k1 is accelerated")
+        if self.name not in ("secp256k1", "p256", "p384"):
+            raise EllipticError("sign_batch: secp256k1, p256 and p384 are accelerated")
         lib = nat.init(self._device)
-        n = len(msgs)
-        e = np.zeros((n, 32), np.uint8); d = np.zeros((n, 32), np.uint8)
+        n, ln = len(msgs), self._len
+        e = np.zeros((n, ln), np.uint8); d = np.zeros((n, ln), np.uint8)
         for i in range(n):
             ev = self._truncate_to_n(msgs[i], msg_bit_length)
-            if ev >> 256:
+            if ev >= self.n:
+                ev -= self.n                                                   # ec/index.js:105-106
+            if ev >> (8 * ln):
                 raise EllipticError("Can not sign message")                    # ec/index.js:136-137
-            e[i] = np.frombuffer(ev.to_bytes(32, "big"), np.uint8)
-            d[i] = np.frombuffer((_bn(privs[i]) % self.n).to_bytes(32, "big"), np.uint8)   # _importPrivate
-        r = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+            e[i] = np.frombuffer(ev.to_bytes(ln, "big"), np.uint8)
+            d[i] = np.frombuffer((_bn(privs[i]) % self.n).to_bytes(ln, "big"), np.uint8)   # _importPrivate
+        r = np.zeros((n, ln), np.uint8); s = np.zeros((n, ln), np.uint8)
         rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
         nat.check(lib.eb200_ecdsa_sign_batch(self._c["id"], n, e.ctypes.data, d.ctypes.data, 1 if canonical else 0,
                                              r.ctypes.data, s.ctypes.data, rec.ctypes.data, st.ctypes.data))

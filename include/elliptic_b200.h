@@ -102,12 +102,13 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream);
 
-/* Batch of EC.prototype.sign (lib/elliptic/ec/index.js:110-186), secp256k1, default hash (sha256) and no
- * `pers` / custom `k`: RFC 6979 nonces from HMAC-DRBG(SHA-256) are generated on the GPU.
- *   e    : n x 32  _truncateToN(msg) (ec/index.js:127), big-endian
- *   priv : n x 32  private scalars as the key pair holds them (reduced mod n at import, ec/key.js:76-82)
+/* Batch of EC.prototype.sign (lib/elliptic/ec/index.js:110-186) on secp256k1, p256 (len = 32) and p384 (len = 48),
+ * with the curve's default hash (sha256 / sha256 / sha384, curves.js:73-107,176-206) and no `pers` / custom `k`:
+ * the RFC 6979 nonces come from HMAC-DRBG over that hash, generated on the GPU.
+ *   e    : n x len  _truncateToN(msg) (ec/index.js:127) including its final `- n`, i.e. e < n, big-endian
+ *   priv : n x len  private scalars as the key pair holds them (reduced mod n at import, ec/key.js:76-82)
  *   flags: EB200_SIGN_CANONICAL = the `canonical` option (s <= n/2, recovery bit flipped)
- *   out_r, out_s : n x 32 big-endian; out_recid : n bytes (recoveryParam)
+ *   out_r, out_s : n x len big-endian; out_recid : n bytes (recoveryParam)
  * status: TRUE for every item (the reference's retry loop runs inside the kernel). */
 #define EB200_SIGN_CANONICAL 1u
 int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,

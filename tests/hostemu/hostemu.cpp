@@ -323,3 +323,35 @@ extern "C" void he_verify_sm(size_t N, const uint8_t* e, const uint8_t* r, const
   u32 acc[SM_WORDS];
   for (size_t i = 0; i < N; i++) status[i] = verify_item_sm<1>(i, N, pub, r, ws.data(), gtab, qtab.data(), acc);
 }
+
+// ---------------------------------------------------------------------------
+// EC.sign on p256 / p384: nonce -> finish -> flagged items through the literal loop
+#include "../../elliptic_b200/csrc/ecdsa_sw_sign.cuh"
+template <class SG, class C>
+static void sw_sign_host(size_t N, const uint8_t* e, const uint8_t* priv, u32 canonical, uint8_t* r, uint8_t* s,
+                         uint8_t* recid, uint8_t* status, int force_slow_every) {
+  typedef SW<C> W;
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)W::GWINDOWS * W::GENTRIES * 2 * W::N);
+    for (int j = 0; j < W::GWINDOWS; j++)
+      for (int i = 0; i < W::GENTRIES; i++) W::gtab_entry(j, i, &gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N]);
+  }
+  std::vector<u32> ws((size_t)SG::WS_WORDS * N), scratch((size_t)SG::SCRATCH_WORDS * N);
+  for (size_t i = 0; i < N; i++) SG::nonce_item(i, N, e, priv, gtab.data(), ws.data(), status);
+  if (force_slow_every)
+    for (size_t i = 0; i < N; i += force_slow_every) {
+      status[i] = 4;
+      typename W::fe one = W::F::one();
+      for (int w = 0; w < W::N; w++) { ws[(size_t)(2 * W::N + w) * N + i] = one.v[w]; ws[(size_t)(3 * W::N + w) * N + i] = w == 0; }
+    }
+  size_t T = (N + SG::BATCH - 1) / SG::BATCH;
+  for (size_t t = 0; t < T; t++) SG::finish_thread(t, T, N, e, priv, canonical, ws.data(), scratch.data(), r, s, recid, status);
+  for (size_t i = 0; i < N; i++)
+    if (status[i] == 4) status[i] = SG::slow_item(i, e, priv, canonical, gtab.data(), r, s, recid);
+}
+extern "C" void he_sw_sign(int curve, size_t N, const uint8_t* e, const uint8_t* priv, u32 canonical, uint8_t* r, uint8_t* s,
+                           uint8_t* recid, uint8_t* status, int force_slow_every) {
+  if (curve == 2) sw_sign_host<SWSign<P256, Sha256W>, P256>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
+  else sw_sign_host<SWSign<P384, Sha384W>, P384>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
+}

@@ -367,3 +367,24 @@ def test_der_import_body_matches_reference(he):
                 assert (int.from_bytes(bytes(r), "big"), int.from_bytes(bytes(s), "big")) == (fit(want[0]), fit(want[1])), der.hex()
         kinds.add(want is not None)
     assert kinds == {True, False}
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48)])
+def test_sw_sign_pipeline_against_oracle(he, name, cid, ln):
+    """EC.sign on p256 (HMAC-DRBG/SHA-256) and p384 (SHA-384): r, s, recoveryParam equal the oracle's, with and
+    without `canonical`, and with items routed through the literal retry loop."""
+    from oracle.ref_py.ec import EC
+    ec = EC(name)
+    rnd = random.Random(15 + cid)
+    items = [(rnd.randrange(ec.n), rnd.randrange(1, ec.n)) for _ in range(18)] + [(0, 1), (ec.n - 1, ec.n - 1)]
+    n = len(items)
+    e = b"".join(x.to_bytes(ln, "big") for x, _ in items)
+    d = b"".join(y.to_bytes(ln, "big") for _, y in items)
+    for canon, every in ((0, 0), (1, 0), (1, 4)):
+        r, s = (ctypes.c_uint8 * (ln * n))(), (ctypes.c_uint8 * (ln * n))()
+        rec, st = (ctypes.c_uint8 * n)(), (ctypes.c_uint8 * n)()
+        he.he_sw_sign(cid, ctypes.c_size_t(n), e, d, canon, r, s, rec, st, every)
+        for i, (ev, dv) in enumerate(items):
+            sig = ec.sign(ev, dv, canonical=bool(canon))
+            assert (int.from_bytes(bytes(r[ln * i:ln * i + ln]), "big"), int.from_bytes(bytes(s[ln * i:ln * i + ln]), "big"),
+                    rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1), (i, canon, every)
