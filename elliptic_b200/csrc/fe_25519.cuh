@@ -106,15 +106,72 @@ EB_HD f25 f25_sqr_inl(const f25& a) {
   f25_reduce512(r.v, t);
   return r;
 }
+#ifndef EB_FE_SQR_INLINE
+#define EB_FE_SQR_INLINE 1     // r01: squarer inlined, multiplier out of line (fewer call-marshalling moves)
+#endif
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__ f25 f25_mul(f25 a, f25 b) { return f25_mul_inl(a, b); }
+#if EB_FE_SQR_INLINE
+EB_HD f25 f25_sqr(const f25& a) { return f25_sqr_inl(a); }
+#else
 __host__ __device__ __noinline__ f25 f25_sqr(f25 a) { return f25_sqr_inl(a); }
+#endif
 #else
 EB_HD f25 f25_mul(const f25& a, const f25& b) { return f25_mul_inl(a, b); }
 EB_HD f25 f25_sqr(const f25& a) { return f25_sqr_inl(a); }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// Device add / sub: the 2^256 = 38 wrap touches limb 0 only unless it carries out of it (38 / 2^32 of
+// the time); that propagation and the second wrap behind it sit in a cold branch (as fe_k256.cuh).
+EB_D f25 f25_add_ptx(const f25& a, const f25& b) {
+  f25 r;
+  const u32 Z = 0;
+  u32 cy, c2;
+  F25_ADD_CC(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) F25_ADDC_CC(r.v[i], a.v[i], b.v[i]);
+  F25_ADDC(cy, Z, Z);
+  u32 kK = (0u - cy) & 38u;
+  F25_ADD_CC(r.v[0], r.v[0], kK);
+  F25_ADDC(c2, Z, Z);
+  if (c2) {
+    u32 c3;
+    F25_ADD_CC(r.v[1], r.v[1], c2);
+#pragma unroll
+    for (int i = 2; i < 8; i++) F25_ADDC_CC(r.v[i], r.v[i], Z);
+    F25_ADDC(c3, Z, Z);
+    r.v[0] += (0u - c3) & 38u;            // wrapped twice: the value is tiny now
+  }
+  return r;
+}
+EB_D f25 f25_sub_ptx(const f25& a, const f25& b) {
+  f25 r;
+  const u32 Z = 0;
+  u32 bw, b2;
+  asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+  for (int i = 1; i < 8; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+  asm volatile("subc.u32 %0, %1, %1;" : "=r"(bw) : "r"(Z));      // 0 or 0xFFFFFFFF
+  u32 kK = bw & 38u;
+  asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(kK));
+  asm volatile("subc.u32 %0, %1, %1;" : "=r"(b2) : "r"(Z));
+  if (b2) {
+    u32 b3;
+    asm volatile("sub.cc.u32 %0, %0, %1;" : "+r"(r.v[1]) : "r"(1u));
+#pragma unroll
+    for (int i = 2; i < 8; i++) asm volatile("subc.cc.u32 %0, %0, %1;" : "+r"(r.v[i]) : "r"(Z));
+    asm volatile("subc.u32 %0, %1, %1;" : "=r"(b3) : "r"(Z));
+    r.v[0] -= b3 & 38u;                   // wrapped below zero twice: the low limb is >= 2^32 - 38
+  }
+  return r;
+}
+#endif
+
 EB_HD f25 f25_add(const f25& a, const f25& b) {
+#if defined(__CUDA_ARCH__)
+  return f25_add_ptx(a, b);
+#endif
   f25 r;
   u32 cy = add_n<8>(r.v, a.v, b.v);
   u32 t[8] = {cy ? 38u : 0u, 0, 0, 0, 0, 0, 0, 0};
@@ -123,6 +180,9 @@ EB_HD f25 f25_add(const f25& a, const f25& b) {
   return r;
 }
 EB_HD f25 f25_sub(const f25& a, const f25& b) {
+#if defined(__CUDA_ARCH__)
+  return f25_sub_ptx(a, b);
+#endif
   f25 r;
   u32 bw = sub_n<8>(r.v, a.v, b.v);
   u32 t[8] = {bw ? 38u : 0u, 0, 0, 0, 0, 0, 0, 0};
