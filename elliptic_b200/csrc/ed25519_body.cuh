@@ -31,11 +31,11 @@ EB_HD ed_ext ed_identity() { ed_ext r; r.x = f25_zero(); r.y = f25_one(); r.z = 
 
 // dbl-2008-hwcd, a = -1  (edwards.js:174-205)
 EB_HD ed_ext ed_dbl_inl(const ed_ext& p) {
-  f25 a = f25_sqr(p.x);
-  f25 b = f25_sqr(p.y);
-  f25 c = f25_dbl(f25_sqr(p.z));
+  f25 a = f25_sqr_hot(p.x);
+  f25 b = f25_sqr_hot(p.y);
+  f25 c = f25_dbl(f25_sqr_hot(p.z));
   f25 d = f25_neg(a);
-  f25 e = f25_sub(f25_sub(f25_sqr(f25_add(p.x, p.y)), a), b);
+  f25 e = f25_sub(f25_sub(f25_sqr_hot(f25_add(p.x, p.y)), a), b);
   f25 g = f25_add(d, b);
   f25 f = f25_sub(g, c);
   f25 h = f25_sub(d, b);
@@ -301,11 +301,11 @@ EB_HD uint8_t x25519_derive_item(size_t i, const uint8_t* priv, const uint8_t* p
     f25 sb = f25_add(bx, bz), db = f25_sub(bx, bz);
     f25 t1 = f25_mul(db, sa);        // (xb - zb)(xa + za)
     f25 t2 = f25_mul(sb, da_);       // (xb + zb)(xa - za)
-    f25 nx = f25_sqr(f25_add(t1, t2));               // * diff.z (= 1)
-    f25 nz = f25_mul(x, f25_sqr(f25_sub(t1, t2)));   // * diff.x
+    f25 nx = f25_sqr_hot(f25_add(t1, t2));               // * diff.z (= 1)
+    f25 nz = f25_mul(x, f25_sqr_hot(f25_sub(t1, t2)));   // * diff.x
     // dbl of a (bit 1) or b (bit 0)
     f25 s = f25_cmov(sb, sa, one), d = f25_cmov(db, da_, one);
-    f25 aa = f25_sqr(s), bb = f25_sqr(d);
+    f25 aa = f25_sqr_hot(s), bb = f25_sqr_hot(d);
     f25 c = f25_sub(aa, bb);
     f25 dx = f25_mul(aa, bb);
     f25 dz = f25_mul(c, f25_add(bb, f25_mul_small(c, 121666u)));

@@ -111,14 +111,16 @@ EB_HD f25 f25_sqr_inl(const f25& a) {
 #endif
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__ f25 f25_mul(f25 a, f25 b) { return f25_mul_inl(a, b); }
-#if EB_FE_SQR_INLINE
-EB_HD f25 f25_sqr(const f25& a) { return f25_sqr_inl(a); }
-#else
 __host__ __device__ __noinline__ f25 f25_sqr(f25 a) { return f25_sqr_inl(a); }
+#if EB_FE_SQR_INLINE
+EB_HD f25 f25_sqr_hot(const f25& a) { return f25_sqr_inl(a); }     // doubling / ladder step only
+#else
+EB_HD f25 f25_sqr_hot(const f25& a) { return f25_sqr(a); }
 #endif
 #else
 EB_HD f25 f25_mul(const f25& a, const f25& b) { return f25_mul_inl(a, b); }
 EB_HD f25 f25_sqr(const f25& a) { return f25_sqr_inl(a); }
+EB_HD f25 f25_sqr_hot(const f25& a) { return f25_sqr_inl(a); }
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -162,14 +162,18 @@ EB_HD fe fe_sqr_inl(const fe& a) {
 #endif                         // call-marshalling moves of 5 of the 7 products in a doubling: 26.95 -> 26.54 ms
 #if defined(__CUDACC__) && EB_FE_OUTLINE
 __host__ __device__ __noinline__ fe fe_mul(fe a, fe b) { return fe_mul_inl(a, b); }
-#if defined(EB_FE_SQR_INLINE) && EB_FE_SQR_INLINE          // experiment: squarer inlined, multiplier out of line
-EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
-#else
 __host__ __device__ __noinline__ fe fe_sqr(fe a) { return fe_sqr_inl(a); }
+// the group-law bodies (jac_dbl_inl / jac_madd_inl) take the squarer inline: 8 of their 18 products then need
+// no call marshalling; everything else (inversion and square-root chains) keeps the out-of-line copy
+#if EB_FE_SQR_INLINE
+EB_HD fe fe_sqr_hot(const fe& a) { return fe_sqr_inl(a); }
+#else
+EB_HD fe fe_sqr_hot(const fe& a) { return fe_sqr(a); }
 #endif
 #else
 EB_HD fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
 EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
+EB_HD fe fe_sqr_hot(const fe& a) { return fe_sqr_inl(a); }
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -35,16 +35,16 @@ EB_HD ge_jac jac_from_aff(const ge_aff& p) {
 // 2*P, a = 0: dbl-2009-l (2M + 5S).  Infinity in -> infinity out (Z3 = 2*Y*Z).
 // (short.js:697-733.)
 EB_HD ge_jac jac_dbl_inl(const ge_jac& p) {
-  fe A = fe_sqr(p.x);
-  fe B = fe_sqr(p.y);
-  fe C = fe_sqr(B);
+  fe A = fe_sqr_hot(p.x);
+  fe B = fe_sqr_hot(p.y);
+  fe C = fe_sqr_hot(B);
   fe t = fe_add(p.x, B);
-  t = fe_sqr(t);
+  t = fe_sqr_hot(t);
   t = fe_sub(t, A);
   t = fe_sub(t, C);
   fe D = fe_dbl(t);
   fe E = fe_mul_small(A, 3);
-  fe F = fe_sqr(E);
+  fe F = fe_sqr_hot(E);
   ge_jac r;
   r.x = fe_sub(F, fe_dbl(D));
   fe C8 = fe_mul_small(C, 8);
@@ -59,16 +59,16 @@ EB_HD ge_jac jac_dbl_aff(const ge_aff& p) { return jac_dbl_inl(jac_from_aff(p));
 // acc + P for Jacobian acc and affine P (8M + 3S), all cases exact.
 // (short.js:569-603.)
 EB_HD ge_jac jac_madd_inl(const ge_jac& a, const ge_aff& p) {
-  fe z2 = fe_sqr(a.z);
+  fe z2 = fe_sqr_hot(a.z);
   fe u2 = fe_mul(p.x, z2);
   fe s2 = fe_mul(fe_mul(p.y, z2), a.z);
   fe h = fe_sub(a.x, u2);
   fe rr = fe_sub(a.y, s2);
-  fe h2 = fe_sqr(h);
+  fe h2 = fe_sqr_hot(h);
   fe h3 = fe_mul(h2, h);
   fe v = fe_mul(a.x, h2);
   ge_jac r;
-  r.x = fe_sub(fe_sub(fe_add(fe_sqr(rr), h3), v), v);
+  r.x = fe_sub(fe_sub(fe_add(fe_sqr_hot(rr), h3), v), v);
   r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(a.y, h3));
   r.z = fe_mul(a.z, h);
   if (fe_is_zero(r.z)) {                       // cold: a == inf, or h == 0
