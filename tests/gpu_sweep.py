@@ -14,7 +14,7 @@ from elliptic_b200.ec import EC
 from elliptic_b200.eddsa import EDDSA
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "ed25519_msgs", "curve25519", "k256_sign", "k256_recover", "k256_mul", "k256_mul_add", "k256_mul_g"]
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["secp256k1", "p256", "p384", "ed25519", "ed25519_msgs", "curve25519", "k256_sign", "k256_recover", "k256_mul", "k256_mul_add", "k256_mul_g", "p256_sign", "p384_sign"]
 CACHE = "/tmp/eb200_cache"
 res = {}
 for name in which:
@@ -53,6 +53,20 @@ for name in which:
                 nat.check(lib.eb200_ecdsa_recover_batch(1, n, ds0["e"].ctypes.data, ds0["r"].ctypes.data, ds0["s"].ctypes.data,
                                                         rid.ctypes.data, out.ctypes.data, st.ctypes.data))
                 return np.where((st == 1) | (st == 2), 1, st).astype(np.uint8)
+    elif name in ("p256_sign", "p384_sign"):
+        cname = name[:4]
+        cid, ln = {"p256": (2, 32), "p384": (3, 48)}[cname]
+        lib = nat.init(0)
+        rng = np.random.default_rng(9)
+        e_in = rng.integers(0, 256, size=(n, ln), dtype=np.uint8); e_in[:, 0] &= 0x7F
+        priv = rng.integers(0, 256, size=(n, ln), dtype=np.uint8); priv[:, 0] &= 0x7F; priv[:, ln - 1] |= 1
+        r_o = np.zeros((n, ln), np.uint8); s_o = np.zeros((n, ln), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
+        ds = {"expected": np.ones(n, np.uint8)}
+
+        def run():
+            nat.check(lib.eb200_ecdsa_sign_batch(cid, n, e_in.ctypes.data, priv.ctypes.data, 0, r_o.ctypes.data,
+                                                 s_o.ctypes.data, rec.ctypes.data, st.ctypes.data))
+            return st
     elif name in ("k256_mul", "k256_mul_add", "k256_mul_g"):
         ds0 = benchdata.gen_ecdsa_verify("secp256k1", n, seed=0xE1110002, cache_dir=CACHE)
         lib = nat.init(0)

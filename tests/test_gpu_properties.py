@@ -174,3 +174,23 @@ def test_openssl_signatures_verify_and_forgeries_do_not(native, name):
         assert (st == 1).all(), np.nonzero(st != 1)[0][:5]
         e2 = e.copy(); e2[:, ln - 1] ^= 0x10
         assert (g.verify_batch_der_packed(e2, ders, pub, fmt) == 0).all()
+
+
+def test_c_abi_argument_and_error_behaviour(native):
+    """The boundary's own contract (include/elliptic_b200.h): empty batches succeed without touching the output,
+    NULL pointers and unknown curves / formats come back as error codes, never as a crash, and the library
+    stays usable afterwards."""
+    from elliptic_b200 import _native as nat
+    lib = nat.init(0)
+    z = np.zeros((4, 64), np.uint8); st = np.full(4, 0xEE, np.uint8)
+    assert lib.eb200_ecdsa_verify_batch(1, 0, None, None, None, None, 0, None) == nat.OK
+    assert lib.eb200_ecdsa_verify_batch(1, 4, None, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, st.ctypes.data) == -3      # EB200_ERR_ARG
+    assert lib.eb200_ecdsa_verify_batch(77, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, st.ctypes.data) == -5  # UNSUPPORTED
+    assert lib.eb200_ecdsa_verify_batch(1, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 9, st.ctypes.data) == -5
+    assert (st == 0xEE).all()
+    assert lib.eb200_ecdsa_sign_batch(4, 4, z.ctypes.data, z.ctypes.data, 0, z.ctypes.data, z.ctypes.data, st.ctypes.data, st.ctypes.data) == -5
+    assert lib.eb200_mul_add_batch(1, 4, None, z.ctypes.data, z.ctypes.data, z.ctypes.data, st.ctypes.data) == -3
+    assert lib.eb200_strerror(-3).decode() == "invalid argument"
+    # all-zero inputs are legal inputs: r = s = 0 -> FALSE for every item
+    assert lib.eb200_ecdsa_verify_batch(1, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, st.ctypes.data) == nat.OK
+    assert (st == 0).all()
