@@ -258,6 +258,23 @@ sw_replay_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restr
   if (i >= N || status[i] != ST_NEEDS_HOST) return;
   status[i] = SWReplay<C>::verify_item(i, e, r, s, pub, tab);
 }
+// EC.recoverPubKey on the non-GLV curves
+template <class C>
+__global__ void __launch_bounds__(128)
+sw_prep_recover_kernel(size_t N, const uint8_t* __restrict__ e, const uint8_t* __restrict__ r, const uint8_t* __restrict__ s,
+                       u32* __restrict__ ws) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) SW<C>::prep_recover_item(i, N, e, r, s, ws);
+}
+template <class C>
+__global__ void __launch_bounds__(128, 2)
+sw_recover_kernel(size_t N, const uint8_t* __restrict__ r, const uint8_t* __restrict__ recid, const u32* __restrict__ ws,
+                  const u32* __restrict__ gtab, u32* __restrict__ qtab, uint8_t* __restrict__ out, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  status[i] = SW<C>::recover_item(i, N, r, recid, ws, gtab, qtab, out);
+}
+
 // EC.sign on p256 / p384 (ecdsa_sw_sign.cuh)
 template <class SG>
 __global__ void __launch_bounds__(128)
@@ -847,38 +864,63 @@ int eb200_ecdsa_verify_batch_der(int curve, size_t n, const uint8_t* e, const ui
 }
 
 // ---- ECDSA public-key recovery (secp256k1) ------------------------------------------------
+}  // extern "C"
+
+template <class C>
+static int sw_recover_launch(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, const uint8_t* d_s, const uint8_t* d_id,
+                             uint8_t* d_out, const WsLayout& L, cudaStream_t st) {
+  unsigned nb = (unsigned)((n + 127) / 128);
+  sw_prep_recover_kernel<C><<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, (u32*)(g.d_ws + L.ws));
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[4], st));
+  sw_recover_kernel<C><<<nb, 128, 0, st>>>(n, d_r, d_id, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(g.ev[5], st));
+  return EB200_OK;
+}
+
+extern "C" {
+
 int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s,
                               const uint8_t* recid, uint8_t* out_xy, uint8_t* status) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   if (!e || !r || !s || !recid || !out_xy || !status) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
   int rc = ensure_table(curve);
   if (rc) return rc;
+  const size_t len = curve_len(curve);
   WsLayout L = ws_layout(curve, n);
-  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (3 * 32 + 1 + 64) + 256))) return rc;
+  if ((rc = grow(&g.d_in, &g.d_in_cap, n * (5 * len + 1) + 256))) return rc;
   if ((rc = grow(&g.d_ws, &g.d_ws_cap, L.total))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
-  uint8_t *d_e = g.d_in, *d_r = d_e + 32 * n, *d_s = d_r + 32 * n, *d_out = d_s + 32 * n, *d_id = d_out + 64 * n;
+  uint8_t *d_e = g.d_in, *d_r = d_e + len * n, *d_s = d_r + len * n, *d_out = d_s + len * n, *d_id = d_out + 2 * len * n;
   cudaStream_t st = g.stream;
   CK(cudaEventRecord(g.ev[0], st));
-  CK(cudaMemcpyAsync(d_e, e, 32 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_r, r, 32 * n, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_s, s, 32 * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_e, e, len * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_r, r, len * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_s, s, len * n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_id, recid, n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
-  size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
-  k256_prep_recover_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_r, d_s, (u32*)(g.d_ws + L.ws), (u32*)(g.d_ws + L.scratch));
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(g.ev[4], st));
-  k256_recover_kernel<<<(unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK), EB_VERIFY_BLOCK, 0, st>>>(
-      n, d_r, d_id, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(g.ev[5], st));
+  if (curve == EB200_CURVE_SECP256K1) {
+    size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;
+    k256_prep_recover_kernel<<<(unsigned)((T + 127) / 128), 128, 0, st>>>(n, d_e, d_r, d_s, (u32*)(g.d_ws + L.ws), (u32*)(g.d_ws + L.scratch));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[4], st));
+    k256_recover_kernel<<<(unsigned)((n + EB_VERIFY_BLOCK - 1) / EB_VERIFY_BLOCK), EB_VERIFY_BLOCK, 0, st>>>(
+        n, d_r, d_id, (u32*)(g.d_ws + L.ws), g.gtab[curve], (u32*)(g.d_ws + L.qtab), d_out, g.d_status);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(g.ev[5], st));
+  } else {
+    rc = curve == EB200_CURVE_P256 ? sw_recover_launch<P256>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st)
+       : curve == EB200_CURVE_P384 ? sw_recover_launch<P384>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st)
+                                   : sw_recover_launch<P521>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st);
+    if (rc) return rc;
+  }
   CK(cudaEventRecord(g.ev[2], st));
-  CK(cudaMemcpyAsync(out_xy, d_out, 64 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out_xy, d_out, 2 * len * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(status, g.d_status, n, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(g.ev[3], st));
   CK(cudaStreamSynchronize(st));

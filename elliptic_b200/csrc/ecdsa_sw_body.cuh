@@ -208,6 +208,26 @@ struct SW {
     ws[(size_t)(2 * N) * cnt_items + i] = flags;
   }
 
+  // recoverPubKey scalars (ec/index.js:250-258): s1 = (n - e) r^-1, s2 = s r^-1 (mod n), with BN.invm's
+  // convention that a multiple of n inverts to 0 (the result is then the point at infinity).  One inversion per
+  // item: recovery is not on the headline path and stays simple.
+  static EB_HD void prep_recover_item(size_t i, size_t cnt_items, const uint8_t* e, const uint8_t* r, const uint8_t* s,
+                                      u32* ws) {
+    typedef typename S::fe sc;
+    const size_t LEN = C::LEN;
+    u32 nmod[N];
+    n_limbs(nmod);
+    sc rv, sv, ev;
+    ldb(rv.v, r + LEN * i); ldb(sv.v, s + LEN * i); ldb(ev.v, e + LEN * i);
+    sc rm = S::to_mont(rv);                              // r mod n, Montgomery form (r < R)
+    sc rinv = S::zero();
+    if (!S::is_zero(rm)) rinv = S::inv(rm);
+    sc u1 = S::mul(ev, rinv);                            // e / r (plain; e < R)
+    if (!is_zero_n<N>(u1.v)) sub_n<N>(u1.v, nmod, u1.v); // (n - e) / r
+    sc u2 = S::mul(sv, rinv);
+    prep_store(i, cnt_items, u1.v, u2.v, 0, ws);
+  }
+
   // k < 2^(8 LEN) -> k mod n.  One conditional subtraction when 2^(8 LEN) <= 2n; p521 (528-bit strings,
   // 521-bit n) goes through the Montgomery round trip x -> xR -> x.
   static EB_HD void reduce_scalar(u32* k) {
@@ -344,6 +364,38 @@ struct SW {
     if (!on_curve(P)) return 4;
     u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
     jac acc = dsm(i, cnt_items, P, flags, ws, gtab, qtab);
+    if (F::is_zero(acc.z)) return 7;
+    store_point(out, i, to_aff(acc));
+    return 1;
+  }
+
+  // EC.prototype.recoverPubKey (ec/index.js:231-259): R = pointFromX(r or r + n, odd) (short.js:187-204, p = 3 mod 4),
+  // Q = s1*G + s2*R.  1 = point written, 7 = infinity, 2 = 'invalid point', 8 = 'Unable to find sencond key candinate'.
+  static EB_HD uint8_t recover_item(size_t i, size_t cnt_items, const uint8_t* r, const uint8_t* recid, const u32* ws,
+                                    const u32* gtab, u32* qtab, uint8_t* out) {
+    const size_t LEN = C::LEN;
+    for (size_t b = 0; b < 2 * LEN; b++) out[2 * LEN * i + b] = 0;
+    u32 j = recid[i];
+    bool odd = j & 1, second = (j >> 1) & 1;
+    fe xr;
+    ldb(xr.v, r + LEN * i);
+    u32 pmn[N];
+    C::p_minus_n(pmn);                                   // p mod n
+    if (second && geq_n<N>(xr.v, pmn)) return 8;
+    if (second) { u32 nmod[N]; n_limbs(nmod); add_n<N>(xr.v, xr.v, nmod); }   // r + n < p < 2^(32N)
+    fe x = F::to_mont(xr);
+    fe y2 = F::add(F::sub(F::mul(F::sqr(x), x), F::add(F::dbl(x), x)), C::b());
+    u32 ex[N];
+    F::Params::mod(ex);                                  // (p + 1) / 4
+    { u32 one[N]; for (int w = 0; w < N; w++) one[w] = w == 0; add_n<N>(ex, ex, one); }
+    for (int k = 0; k < N; k++) ex[k] = (ex[k] >> 2) | ((k + 1 < N ? ex[k + 1] : 0u) << 30);
+    fe y = F::pow(y2, ex);
+    if (!F::eq(F::sqr(y), y2)) return 2;
+    fe yp = F::from_mont(y);
+    if (((yp.v[0] & 1) != 0) != odd) y = F::neg(y);
+    aff R; R.x = x; R.y = y;
+    u32 flags = ws[(size_t)(2 * N) * cnt_items + i];
+    jac acc = dsm(i, cnt_items, R, flags, ws, gtab, qtab);
     if (F::is_zero(acc.z)) return 7;
     store_point(out, i, to_aff(acc));
     return 1;

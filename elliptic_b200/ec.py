@@ -320,26 +320,28 @@ class EC:
         """Batch of EC.prototype.recoverPubKey (ec/index.js:231-259).  msgs as `new BN(msg)` takes them
         (int / hex / bytes, NOT truncated), sigs as Signature takes them, js the recovery params.
         Returns (points, statuses): points[i] = (x, y), None for the point at infinity / a throw."""
-        if self.name != "secp256k1":
-            raise EllipticError("recover_pub_key_batch: only secp256k1 is accelerated")
+        if self.name not in ("secp256k1", "p256", "p384", "p521"):
+            raise EllipticError("recover_pub_key_batch: short curves only")
         lib = nat.init(self._device)
-        n = len(msgs)
-        e = np.zeros((n, 32), np.uint8); r = np.zeros((n, 32), np.uint8); s = np.zeros((n, 32), np.uint8)
+        n, ln = len(msgs), self._len
+        e = np.zeros((n, ln), np.uint8); r = np.zeros((n, ln), np.uint8); s = np.zeros((n, ln), np.uint8)
         rid = np.zeros(n, np.uint8)
         for i in range(n):
             if (3 & js[i]) != js[i]:
                 raise EllipticError("The recovery param is more than two bits")      # ec/index.js:232
             rv, sv = self._signature_enc(sigs[i], enc)
             ev = _bn(msgs[i]) if not isinstance(msgs[i], (bytes, bytearray, list, tuple)) else int.from_bytes(_to_array(msgs[i]), "big")
-            e[i] = np.frombuffer((ev % self.n).to_bytes(32, "big"), np.uint8)
-            r[i] = np.frombuffer((rv % (1 << 256)).to_bytes(32, "big"), np.uint8)
-            s[i] = np.frombuffer((sv % self.n).to_bytes(32, "big"), np.uint8)
+            if rv >> (8 * ln):
+                raise NeedsReferencePath("r does not fit the curve's field width")
+            e[i] = np.frombuffer((ev % self.n).to_bytes(ln, "big"), np.uint8)
+            r[i] = np.frombuffer(rv.to_bytes(ln, "big"), np.uint8)
+            s[i] = np.frombuffer((sv % self.n).to_bytes(ln, "big"), np.uint8)
             rid[i] = js[i]
-        out = np.zeros((n, 64), np.uint8)
+        out = np.zeros((n, 2 * ln), np.uint8)
         st = np.zeros(n, np.uint8)
         nat.check(lib.eb200_ecdsa_recover_batch(self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data,
                                                 rid.ctypes.data, out.ctypes.data, st.ctypes.data))
-        pts = [(int.from_bytes(out[i, :32].tobytes(), "big"), int.from_bytes(out[i, 32:].tobytes(), "big"))
+        pts = [(int.from_bytes(out[i, :ln].tobytes(), "big"), int.from_bytes(out[i, ln:].tobytes(), "big"))
                if st[i] == nat.ST_TRUE else None for i in range(n)]
         return pts, st
 

@@ -114,7 +114,8 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
 int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,
                            uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status);
 
-/* Batch of EC.prototype.recoverPubKey (lib/elliptic/ec/index.js:231-259), secp256k1:
+/* Batch of EC.prototype.recoverPubKey (lib/elliptic/ec/index.js:231-259) on secp256k1 / p256 / p384 / p521
+ * (len = 32 / 32 / 48 / 66 in place of the 32 and 64 below):
  *   e     : n x 32  `new BN(msg)` reduced mod n (NOT truncated -- the reference does not truncate here)
  *   r, s  : n x 32  signature halves (no range check in the reference: r = 0 yields the point at infinity)
  *   recid : n bytes, the recovery parameter j in 0..3 (bit 0 = y parity, bit 1 = use r + n)

@@ -355,3 +355,25 @@ extern "C" void he_sw_sign(int curve, size_t N, const uint8_t* e, const uint8_t*
   if (curve == 2) sw_sign_host<SWSign<P256, Sha256W>, P256>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
   else sw_sign_host<SWSign<P384, Sha384W>, P384>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
 }
+
+// EC.recoverPubKey on p256 / p384 / p521
+template <class C>
+static void sw_recover_host(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* recid,
+                            uint8_t* out, uint8_t* status) {
+  typedef SW<C> W;
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)W::GWINDOWS * W::GENTRIES * 2 * W::N);
+    for (int j = 0; j < W::GWINDOWS; j++)
+      for (int i = 0; i < W::GENTRIES; i++) W::gtab_entry(j, i, &gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N]);
+  }
+  std::vector<u32> ws((size_t)W::PREP_WORDS * N), qtab((size_t)W::QTAB_WORDS * N);
+  for (size_t i = 0; i < N; i++) W::prep_recover_item(i, N, e, r, s, ws.data());
+  for (size_t i = 0; i < N; i++) status[i] = W::recover_item(i, N, r, recid, ws.data(), gtab.data(), qtab.data(), out);
+}
+extern "C" void he_sw_recover(int curve, size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* recid,
+                              uint8_t* out, uint8_t* status) {
+  if (curve == 2) sw_recover_host<P256>(N, e, r, s, recid, out, status);
+  else if (curve == 6) sw_recover_host<P521>(N, e, r, s, recid, out, status);
+  else sw_recover_host<P384>(N, e, r, s, recid, out, status);
+}

@@ -6,12 +6,14 @@ P = 2**256 - 2**32 - 977
 
 def rec_items(ec, seed=12, count=60):
     n = ec.n
+    P = ec.curve.p
+    mbits = min(n.bit_length() - 1, 512)        # messages _truncateToN leaves alone
     rnd = random.Random(seed)
     items, truth = [], {}
     for t in range(count):
         d = rnd.randrange(1, n)
-        m = rnd.randrange(2**256)
-        sig = ec.sign(m.to_bytes(32, "big"), d)
+        m = rnd.randrange(2**mbits)
+        sig = ec.sign(m, d)
         Q = ec.g.mul(d)
         for j in range(4):
             if j == sig.recovery_param:

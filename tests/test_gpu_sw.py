@@ -269,3 +269,22 @@ def test_sign_batch_matches_reference_rfc6979(native, name):
             assert (got["r"], got["s"]) == (int(c["r"], 16), int(c["s"], 16)), c
             seen += 1
     assert seen >= 1
+
+
+@pytest.mark.parametrize("name", ["p256", "p384", "p521"])
+def test_recover_pub_key_parity(native, name):
+    """EC.recoverPubKey on the NIST curves (ec/index.js:231-259): all four recovery params of real signatures,
+    the second-key throw, x without a square root, r = 0 (point at infinity); the signer's key comes back for
+    the signature's own recovery param."""
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    from rec_items import rec_items, rec_expected
+    ec = EC(name)
+    items, truth = rec_items(ec, count=40 if name != "p521" else 10)
+    gec = GpuEC(name)
+    pts, st = gec.recover_pub_key_batch([it[0] for it in items], [{"r": it[1] or "00", "s": it[2] or "00"} for it in items],
+                                        [it[3] for it in items])
+    for i, it in enumerate(items):
+        assert (int(st[i]), pts[i]) == rec_expected(ec, it), (i, it[3])
+        if i in truth:
+            assert pts[i] == truth[i]

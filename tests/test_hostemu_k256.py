@@ -388,3 +388,25 @@ def test_sw_sign_pipeline_against_oracle(he, name, cid, ln):
             sig = ec.sign(ev, dv, canonical=bool(canon))
             assert (int.from_bytes(bytes(r[ln * i:ln * i + ln]), "big"), int.from_bytes(bytes(s[ln * i:ln * i + ln]), "big"),
                     rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1), (i, canon, every)
+
+
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+def test_sw_recover_pub_key_body_against_oracle(he, name, cid, ln):
+    from oracle.ref_py.ec import EC
+    from rec_items import rec_items, rec_expected
+    ec = EC(name)
+    items, truth = rec_items(ec, count=6 if ln < 66 else 3)
+    n = len(items)
+    e = b"".join((it[0] % ec.n).to_bytes(ln, "big") for it in items)
+    r = b"".join(it[1].to_bytes(ln, "big") for it in items)
+    s = b"".join((it[2] % ec.n).to_bytes(ln, "big") for it in items)
+    out, st = (ctypes.c_uint8 * (2 * ln * n))(), (ctypes.c_uint8 * n)()
+    he.he_sw_recover(cid, ctypes.c_size_t(n), e, r, s, bytes(it[3] for it in items), out, st)
+    seen = set()
+    for i, it in enumerate(items):
+        pt = (int.from_bytes(bytes(out[2 * ln * i:2 * ln * i + ln]), "big"), int.from_bytes(bytes(out[2 * ln * i + ln:2 * ln * (i + 1)]), "big"))
+        assert (st[i], pt if st[i] == 1 else None) == rec_expected(ec, it), i
+        if i in truth:
+            assert st[i] == 1 and pt == truth[i]
+        seen.add(int(st[i]))
+    assert {1, 2, 7, 8} <= seen
