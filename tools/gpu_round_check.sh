@@ -8,4 +8,5 @@ timeout 1200 python tests/gpu_sweep.py 1048576 secp256k1,p256,p384,ed25519,ed255
 timeout 600 python tests/gpu_sweep.py 262144 p521 > gpurun_out/sweep_p521.log 2>&1; cut -c1-230 gpurun_out/sweep_p521.log | tail -1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k256_verify_kernel -s 2 -c 1 -o gpurun_out/verify_full python tests/gpu_quick.py 1048576 > gpurun_out/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ed25519_verify_kernel -s 1 -c 1 -o gpurun_out/ed25519_full python tests/gpu_sweep.py 262144 ed25519 > gpurun_out/ncu_ed.log 2>&1
 ls gpurun_out | tr '\n' ' '
