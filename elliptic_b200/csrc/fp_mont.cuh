@@ -176,7 +176,56 @@ struct Fp {
   }
   static EB_HD fe sqr(const fe& a) { return mul(a, a); }
 
+#if defined(__CUDA_ARCH__)
+  // Device add / sub for moduli whose top limb is 0xFFFFFFFF (p256, p384 and their group orders): a carry out of
+  // a + b is undone by adding R - p under a mask, and a sum in [p, R) can only occur when its top limb is all ones
+  // (2^-32 of the time), which is left to a cold branch; a borrow out of a - b is undone by adding p under a mask.
+  // No compare-and-select chain on the common path.
+  static EB_D fe add_fast(const fe& a, const fe& b) {
+    u32 p[N], rp[N];
+    P::mod(p); P::r1(rp);                                  // R - p == R mod p because p > R / 2
+    fe r;
+    const u32 Z = 0;
+    u32 cy;
+    asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+    for (int i = 1; i < N; i++) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+    asm volatile("addc.u32 %0, %1, %1;" : "=r"(cy) : "r"(Z));
+    u32 mask = 0u - cy;
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(rp[0] & mask));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.v[i]) : "r"(rp[i] & mask));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.v[N - 1]) : "r"(rp[N - 1] & mask));
+    if (!cy && r.v[N - 1] == 0xffffffffu) {                // cold: the sum may lie in [p, R)
+      fe d;
+      u32 bw = sub_n<N>(d.v, r.v, p);
+      if (!bw) r = d;
+    }
+    return r;
+  }
+  static EB_D fe sub_fast(const fe& a, const fe& b) {
+    u32 p[N];
+    P::mod(p);
+    fe r;
+    const u32 Z = 0;
+    u32 bw;
+    asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r.v[0]) : "r"(a.v[0]), "r"(b.v[0]));
+#pragma unroll
+    for (int i = 1; i < N; i++) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r.v[i]) : "r"(a.v[i]), "r"(b.v[i]));
+    asm volatile("subc.u32 %0, %1, %1;" : "=r"(bw) : "r"(Z));        // 0 or 0xFFFFFFFF
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(r.v[0]) : "r"(p[0] & bw));
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(r.v[i]) : "r"(p[i] & bw));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(r.v[N - 1]) : "r"(p[N - 1] & bw));
+    return r;
+  }
+  static EB_D bool top_limb_all_ones() { u32 p[N]; P::mod(p); return p[N - 1] == 0xffffffffu; }
+#endif
+
   static EB_HD fe add(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__)
+    if (top_limb_all_ones()) return add_fast(a, b);
+#endif
     u32 p[N]; P::mod(p);
     fe r, d;
     u32 cy = add_n<N>(r.v, a.v, b.v);
@@ -187,6 +236,9 @@ struct Fp {
     return r;
   }
   static EB_HD fe sub(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__)
+    if (top_limb_all_ones()) return sub_fast(a, b);
+#endif
     u32 p[N]; P::mod(p);
     fe r, d;
     u32 bw = sub_n<N>(r.v, a.v, b.v);
