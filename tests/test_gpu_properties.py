@@ -194,3 +194,30 @@ def test_c_abi_argument_and_error_behaviour(native):
     # all-zero inputs are legal inputs: r = s = 0 -> FALSE for every item
     assert lib.eb200_ecdsa_verify_batch(1, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, st.ctypes.data) == nat.OK
     assert (st == 0).all()
+
+
+def test_chunked_host_pipeline_equals_single_launch(native):
+    """eb200_ecdsa_verify_batch splits batches of 2^18 and more into chunks on two alternating compute streams
+    with per-chunk workspaces; an odd-sized batch must give the generator's statuses and exactly the statuses
+    of the unchunked path (EB200_CHUNKS=1), for every chunk count the knob allows."""
+    import os
+    import benchdata
+    from elliptic_b200.ec import EC as GpuEC
+    n = (1 << 18) + 777
+    ds = benchdata.gen_secp256k1_verify(n, cache_dir="/tmp/eb200_cache")
+    g = GpuEC("secp256k1")
+    old = os.environ.get("EB200_CHUNKS")
+    try:
+        res = {}
+        for chunks in ("1", "3", "4", "7", "16"):
+            os.environ["EB200_CHUNKS"] = chunks
+            res[chunks] = g.verify_batch_packed(ds["e"], ds["r"], ds["s"], ds["pub"]).copy()
+        os.environ.pop("EB200_CHUNKS")
+        res["default"] = g.verify_batch_packed(ds["e"], ds["r"], ds["s"], ds["pub"]).copy()
+    finally:
+        if old is None:
+            os.environ.pop("EB200_CHUNKS", None)
+        else:
+            os.environ["EB200_CHUNKS"] = old
+    for k, st in res.items():
+        assert np.array_equal(st, ds["expected"]), k
