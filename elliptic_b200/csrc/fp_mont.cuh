@@ -223,7 +223,7 @@ struct Fp {
 #endif
 
   static EB_HD fe add(const fe& a, const fe& b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(EB_MONT_FAST_ADDSUB) && EB_MONT_FAST_ADDSUB   // opt-in until re-verified on the GPU
     if (top_limb_all_ones()) return add_fast(a, b);
 #endif
     u32 p[N]; P::mod(p);
@@ -236,7 +236,7 @@ struct Fp {
     return r;
   }
   static EB_HD fe sub(const fe& a, const fe& b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(EB_MONT_FAST_ADDSUB) && EB_MONT_FAST_ADDSUB
     if (top_limb_all_ones()) return sub_fast(a, b);
 #endif
     u32 p[N]; P::mod(p);
