@@ -14,7 +14,7 @@ OK, ERR_NO_DEVICE, ERR_CUDA, ERR_ARG, ERR_NOT_INIT, ERR_UNSUPPORTED = 0, -1, -2,
 ST_FALSE, ST_TRUE, ST_THROW_INVALID_POINT, ST_THROW_NOT_VALIDATED, ST_NEEDS_HOST, ST_THROW_ASSERT, \
     ST_THROW_POINT_FORMAT = range(7)
 ST_INFINITY, ST_THROW_SECOND_KEY, ST_THROW_SIG_FORMAT = 7, 8, 9
-CURVE_SECP256K1, CURVE_P256, CURVE_P384, CURVE_ED25519, CURVE_CURVE25519, CURVE_P521 = 1, 2, 3, 4, 5, 6
+CURVE_SECP256K1, CURVE_P256, CURVE_P384, CURVE_ED25519, CURVE_CURVE25519, CURVE_P521, CURVE_P192, CURVE_P224 = 1, 2, 3, 4, 5, 6, 7, 8
 PUB_XY, PUB_SEC1_65, PUB_SEC1_33 = 0, 1, 2
 
 EXPORTS = [

@@ -15,6 +15,11 @@
 #include "der_sig.cuh"
 #include "ecdsa_k256_smem.cuh"
 #include "ecdsa_sw_sign.cuh"
+
+// Calls F(curve-parameter type) for the non-GLV short curve `curve`.
+#define SW_DISPATCH(curve, F)                                                                    \
+  ((curve) == EB200_CURVE_P256 ? F(P256) : (curve) == EB200_CURVE_P384 ? F(P384) :               \
+   (curve) == EB200_CURVE_P521 ? F(P521) : (curve) == EB200_CURVE_P192 ? F(P192) : F(P224))
 #include "ecdsa_k256_sign.cuh"
 #include "ecdsa_sw_body.cuh"
 #include "ed25519_body.cuh"
@@ -358,10 +363,9 @@ __global__ void __launch_bounds__(128) sw_decode_pub_kernel(size_t N, const uint
     W::ldb(t.v, p + 1);
     typename F::fe x = F::to_mont(t);
     typename F::fe y2 = F::add(F::sub(F::mul(F::sqr(x), x), F::add(F::dbl(x), x)), C::b());
-    u32 e[NL]; F::Params::mod(e);                     // (p+1)/4: p = 3 mod 4 for p256, p384 and p521
-    { u32 one[NL] = {1}; add_n<NL>(e, e, one); }
-    for (int k = 0; k < NL; k++) e[k] = (e[k] >> 2) | ((k + 1 < NL ? e[k + 1] : 0u) << 30);
-    typename F::fe y = F::pow(y2, e);
+    typename F::fe y = F::zero();
+    uint8_t ss = W::sqrt_ref(y2, &y);                 // Red.sqrt: a^((p+1)/4), or Tonelli-Shanks on p224
+    if (!st && ss) st = ss;
     if (!st && !F::eq(F::sqr(y), y2)) st = ST_THROW_INVALID_POINT;
     typename F::fe yp = F::from_mont(y);
     bool odd = tag == 3;
@@ -447,8 +451,8 @@ struct Ctx {
   bool ready = false;
   int device = -1;
   cudaStream_t stream = nullptr, stream2 = nullptr, copy_stream = nullptr;
-  u32* gtab[8] = {};
-  u32* sw_replay_tab[8] = {};         // p256/p384: the reference's wnd-8 NAF table of G
+  u32* gtab[16] = {};
+  u32* sw_replay_tab[16] = {};         // p256/p384: the reference's wnd-8 NAF table of G
   u32* replay_tab = nullptr;          // secp256k1: the reference's wnd-7 NAF table of G and its beta image
   uint8_t* d_in = nullptr; size_t d_in_cap = 0;
   uint8_t* d_ws = nullptr; size_t d_ws_cap = 0;
@@ -478,14 +482,17 @@ int grow(uint8_t** p, size_t* cap, size_t need) {
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t fe_len(int curve) {   // field-element bytes for the selftest hooks (also the 25519 curves)
-  return (curve == EB200_CURVE_P384) ? 48 : (curve == EB200_CURVE_P521) ? 72 :     // 18 limbs
-         (curve >= EB200_CURVE_SECP256K1 && curve <= EB200_CURVE_CURVE25519) ? 32 : 0;
+  if (curve == EB200_CURVE_P192) return 24;
+  return (curve == EB200_CURVE_P384) ? 48 : (curve == EB200_CURVE_P521) ? 72 :     // 18 limbs; p224 = 8 limbs
+         ((curve >= EB200_CURVE_SECP256K1 && curve <= EB200_CURVE_CURVE25519) || curve == EB200_CURVE_P224) ? 32 : 0;
 }
 size_t curve_len(int curve) {
   switch (curve) {
     case EB200_CURVE_SECP256K1: case EB200_CURVE_P256: return 32;
     case EB200_CURVE_P384: return 48;
     case EB200_CURVE_P521: return 66;
+    case EB200_CURVE_P192: return 24;
+    case EB200_CURVE_P224: return 28;
     default: return 0;
   }
 }
@@ -498,9 +505,11 @@ struct WsLayout { size_t ws, scratch, qtab, xy, pre, total; };
 WsLayout ws_layout(int curve, size_t n) {
   size_t prep_words, scratch_words, qtab_words, len = curve_len(curve);
   if (curve == EB200_CURVE_SECP256K1) { prep_words = PREP_WORDS; scratch_words = 8; qtab_words = QTAB_WORDS; }
-  else if (curve == EB200_CURVE_P256) { prep_words = SW<P256>::PREP_WORDS; scratch_words = 8; qtab_words = SW<P256>::QTAB_WORDS; }
-  else if (curve == EB200_CURVE_P384) { prep_words = SW<P384>::PREP_WORDS; scratch_words = 12; qtab_words = SW<P384>::QTAB_WORDS; }
-  else { prep_words = SW<P521>::PREP_WORDS; scratch_words = 18; qtab_words = SW<P521>::QTAB_WORDS; }
+  else {
+#define EB_WS(C) (prep_words = SW<C>::PREP_WORDS, scratch_words = SW<C>::N, qtab_words = SW<C>::QTAB_WORDS, 0)
+    (void)SW_DISPATCH(curve, EB_WS);
+#undef EB_WS
+  }
   WsLayout L;
   L.ws = 0;
   L.scratch = align256(L.ws + prep_words * n * 4);
@@ -538,9 +547,12 @@ int ensure_table(int curve) {
     CK(cudaStreamSynchronize(g.stream));
     return EB200_OK;
   }
-  if (curve == EB200_CURVE_P256) return sw_ensure_table<P256>(curve);
-  if (curve == EB200_CURVE_P384) return sw_ensure_table<P384>(curve);
-  if (curve == EB200_CURVE_P521) return sw_ensure_table<P521>(curve);
+  if (curve == EB200_CURVE_P256 || curve == EB200_CURVE_P384 || curve == EB200_CURVE_P521 || curve == EB200_CURVE_P192 ||
+      curve == EB200_CURVE_P224) {
+#define EB_ENS(C) sw_ensure_table<C>(curve)
+    return SW_DISPATCH(curve, EB_ENS);
+#undef EB_ENS
+  }
   if (curve == EB200_CURVE_ED25519) {
     if (g.gtab[curve]) return EB200_OK;
     size_t entries = (size_t)ED_GWINDOWS * ED_GENTRIES;
@@ -587,9 +599,11 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     uint8_t* dxy = d_workspace + L.xy;
     uint8_t* dpre = d_workspace + L.pre;
     if (curve == EB200_CURVE_SECP256K1) k256_decode_pub_kernel<<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
-    else if (curve == EB200_CURVE_P256) sw_decode_pub_kernel<P256><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
-    else if (curve == EB200_CURVE_P384) sw_decode_pub_kernel<P384><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
-    else sw_decode_pub_kernel<P521><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre);
+    else {
+#define EB_DEC(C) (sw_decode_pub_kernel<C><<<nb, 128, 0, st>>>(n, d_pub, pub_fmt, dxy, dpre), 0)
+      (void)SW_DISPATCH(curve, EB_DEC);
+#undef EB_DEC
+    }
     CK(cudaGetLastError());
     xy = dxy; pre = dpre; cnt++;
   }
@@ -610,9 +624,9 @@ int launch_verify(int curve, size_t n, const uint8_t* d_e, const uint8_t* d_r, c
     k256_replay_kernel<<<nb, 128, 0, st>>>(n, d_e, d_r, d_s, xy, g.replay_tab, d_status);
     cnt++;
   } else {
-    int rc = curve == EB200_CURVE_P256 ? sw_launch_verify<P256>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1)
-           : curve == EB200_CURVE_P384 ? sw_launch_verify<P384>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1)
-                                       : sw_launch_verify<P521>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1);
+#define EB_VER(C) sw_launch_verify<C>(curve, n, d_e, d_r, d_s, xy, pre, ws, scratch, qtab, d_status, st, pb, nb, ev_main0, &ev_main1)
+    int rc = SW_DISPATCH(curve, EB_VER);
+#undef EB_VER
     if (rc) return rc;
     cnt++;
   }
@@ -662,8 +676,8 @@ int eb200_init(int device) {
     if (!g.ev_k1[i]) CK(cudaEventCreate(&g.ev_k1[i]));
     if (!g.ev_done[i]) CK(cudaEventCreate(&g.ev_done[i]));
   }
-  for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
-  for (int c = 0; c < 8; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
+  for (int c = 0; c < 16; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  for (int c = 0; c < 16; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
   if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   g.device = device;
   g.ready = true;
@@ -677,8 +691,8 @@ int eb200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!g.ready) return EB200_OK;
   cudaSetDevice(g.device);
-  for (int c = 0; c < 8; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
-  for (int c = 0; c < 8; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
+  for (int c = 0; c < 16; c++) if (g.gtab[c]) { cudaFree(g.gtab[c]); g.gtab[c] = nullptr; }
+  for (int c = 0; c < 16; c++) if (g.sw_replay_tab[c]) { cudaFree(g.sw_replay_tab[c]); g.sw_replay_tab[c] = nullptr; }
   if (g.replay_tab) { cudaFree(g.replay_tab); g.replay_tab = nullptr; }
   cudaFree(g.d_in); g.d_in = nullptr; g.d_in_cap = 0;
   cudaFree(g.d_ws); g.d_ws = nullptr; g.d_ws_cap = 0;
@@ -914,9 +928,9 @@ int eb200_ecdsa_recover_batch(int curve, size_t n, const uint8_t* e, const uint8
     CK(cudaGetLastError());
     CK(cudaEventRecord(g.ev[5], st));
   } else {
-    rc = curve == EB200_CURVE_P256 ? sw_recover_launch<P256>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st)
-       : curve == EB200_CURVE_P384 ? sw_recover_launch<P384>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st)
-                                   : sw_recover_launch<P521>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st);
+#define EB_REC(C) sw_recover_launch<C>(curve, n, d_e, d_r, d_s, d_id, d_out, L, st)
+    rc = SW_DISPATCH(curve, EB_REC);
+#undef EB_REC
     if (rc) return rc;
   }
   CK(cudaEventRecord(g.ev[2], st));
@@ -988,12 +1002,10 @@ static int mul_add_common(int curve, size_t n, const uint8_t* k1, const uint8_t*
   CK(cudaMemcpyAsync(d_k2, k2, len * n, cudaMemcpyHostToDevice, st));
   if (pts) CK(cudaMemcpyAsync(d_pts, pts, 2 * len * n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(g.ev[1], st));
-  if (curve == EB200_CURVE_P256) {
-    if ((rc = sw_mul_add_launch<P256>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
-  } else if (curve == EB200_CURVE_P384) {
-    if ((rc = sw_mul_add_launch<P384>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
-  } else if (curve == EB200_CURVE_P521) {
-    if ((rc = sw_mul_add_launch<P521>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive))) return rc;
+  if (curve != EB200_CURVE_SECP256K1) {
+#define EB_MA(C) sw_mul_add_launch<C>(curve, n, k1 ? d_k1 : nullptr, d_k2, pts ? d_pts : nullptr, d_out, L, st, &launches, derive)
+    if ((rc = SW_DISPATCH(curve, EB_MA))) return rc;
+#undef EB_MA
   } else if (!pts) {
     CK(cudaEventRecord(g.ev[4], st));
     k256_mul_g_kernel<<<nb, 128, 0, st>>>(n, d_k2, g.gtab[curve], d_out, g.d_status);
@@ -1294,10 +1306,12 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
   CK(cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, g.stream));
   unsigned nb = (unsigned)((n + 127) / 128);
   if (curve == EB200_CURVE_SECP256K1) k256_selftest_fe_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
-  else if (curve == EB200_CURVE_P256) sw_selftest_fe_kernel<P256><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
   else if (curve == EB200_CURVE_ED25519 || curve == EB200_CURVE_CURVE25519) f25_selftest_kernel<<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
-  else if (curve == EB200_CURVE_P521) sw_selftest_fe_kernel<P521><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
-  else sw_selftest_fe_kernel<P384><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout);
+  else {
+#define EB_ST(C) (sw_selftest_fe_kernel<C><<<nb, 128, 0, g.stream>>>(op, n, da, db, dout), 0)
+    (void)SW_DISPATCH(curve, EB_ST);
+#undef EB_ST
+  }
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
@@ -1308,9 +1322,11 @@ int eb200_selftest_fe(int curve, int op, size_t n, const uint32_t* a, const uint
 int eb200_selftest_gtab_dims(int curve, int* windows, int* entries, int* wbits) {
   if (!windows || !entries || !wbits) return EB200_ERR_ARG;
   if (curve == EB200_CURVE_SECP256K1) { *windows = GTAB_WINDOWS; *entries = GTAB_ENTRIES; *wbits = GTAB_W; }
-  else if (curve == EB200_CURVE_P256) { *windows = SW<P256>::GWINDOWS; *entries = SW<P256>::GENTRIES; *wbits = SW<P256>::GW; }
-  else if (curve == EB200_CURVE_P384) { *windows = SW<P384>::GWINDOWS; *entries = SW<P384>::GENTRIES; *wbits = SW<P384>::GW; }
-  else if (curve == EB200_CURVE_P521) { *windows = SW<P521>::GWINDOWS; *entries = SW<P521>::GENTRIES; *wbits = SW<P521>::GW; }
+  else if (curve_len(curve)) {
+#define EB_DIM(C) (*windows = SW<C>::GWINDOWS, *entries = SW<C>::GENTRIES, *wbits = SW<C>::GW, 0)
+    (void)SW_DISPATCH(curve, EB_DIM);
+#undef EB_DIM
+  }
   else return EB200_ERR_UNSUPPORTED;
   return EB200_OK;
 }

@@ -127,6 +127,46 @@ struct SW {
     return r;
   }
 
+  // Red.prototype.sqrt (bn.js, dist/elliptic.js:7177-7232) on a Montgomery-form operand.  p = 3 mod 4: a^((p+1)/4).
+  // p = 1 mod 4 (p224): Tonelli-Shanks with the reference's own non-residue; for a non-residue its
+  // `assert(i < m)` fires (status 5, 'Assertion failed') before the caller's own y^2 check can.
+  // Returns 0 with a candidate root (the caller still squares it), or 5.
+  static EB_HD uint8_t sqrt_ref(const fe& a, fe* out) {
+    u32 pm[N];
+    F::Params::mod(pm);
+    if ((pm[0] & 3) == 3) {
+      u32 one[N];
+      for (int w = 0; w < N; w++) one[w] = w == 0;
+      add_n<N>(pm, pm, one);
+      for (int k = 0; k < N; k++) pm[k] = (pm[k] >> 2) | ((k + 1 < N ? pm[k + 1] : 0u) << 30);
+      *out = F::pow(a, pm);
+      return 0;
+    }
+    if (F::is_zero(a)) { *out = F::zero(); return 0; }
+    u32 q[N], q1h[N];
+    C::ts_q(q); C::ts_q1h(q1h);
+    fe c = C::ts_c();
+    fe r = F::pow(a, q1h), t = F::pow(a, q);
+    const fe one = F::one();
+    int mm = C::TS_S;
+    while (!F::eq(t, one)) {
+      fe tmp = t;
+      int i = 0;
+      while (!F::eq(tmp, one)) {
+        tmp = F::sqr(tmp);
+        if (++i >= mm) return 5;
+      }
+      fe b = c;
+      for (int k = 0; k < mm - i - 1; k++) b = F::sqr(b);
+      r = F::mul(r, b);
+      c = F::sqr(b);
+      t = F::mul(t, c);
+      mm = i;
+    }
+    *out = r;
+    return 0;
+  }
+
   // y^2 == x^3 - 3x + b  (ShortCurve.validate, short.js:206-216)
   static EB_HD bool on_curve(const aff& p) {
     fe x3 = F::mul(F::sqr(p.x), p.x);
@@ -385,11 +425,8 @@ struct SW {
     if (second) { u32 nmod[N]; n_limbs(nmod); add_n<N>(xr.v, xr.v, nmod); }   // r + n < p < 2^(32N)
     fe x = F::to_mont(xr);
     fe y2 = F::add(F::sub(F::mul(F::sqr(x), x), F::add(F::dbl(x), x)), C::b());
-    u32 ex[N];
-    F::Params::mod(ex);                                  // (p + 1) / 4
-    { u32 one[N]; for (int w = 0; w < N; w++) one[w] = w == 0; add_n<N>(ex, ex, one); }
-    for (int k = 0; k < N; k++) ex[k] = (ex[k] >> 2) | ((k + 1 < N ? ex[k + 1] : 0u) << 30);
-    fe y = F::pow(y2, ex);
+    fe y;
+    if (uint8_t ss = sqrt_ref(y2, &y)) return ss;
     if (!F::eq(F::sqr(y), y2)) return 2;
     fe yp = F::from_mont(y);
     if (((yp.v[0] & 1) != 0) != odd) y = F::neg(y);

@@ -281,8 +281,10 @@ struct Fp {
   }
   // a^(p-2): inverse (0 -> 0, like bn.js _invmp(0), dist:6568-6579)
   static EB_HD fe inv(const fe& a) {
-    u32 e[N]; P::mod(e);
-    e[0] -= 2;  // p is odd and > 2: no borrow
+    u32 e[N], two[N];
+    P::mod(e);
+    for (int i = 0; i < N; i++) two[i] = i == 0 ? 2u : 0u;
+    sub_n<N>(e, e, two);    // full borrow chain: p224's lowest limb is 1
     return pow(a, e);
   }
 };

@@ -30,7 +30,12 @@ _CURVES = {
     "p521": dict(id=nat.CURVE_P521, len=66,
                  n=0x1fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
                  p=2**521 - 1),
+    "p192": dict(id=nat.CURVE_P192, len=24, n=0xffffffffffffffffffffffff99def836146bc9b1b4d22831, p=0xfffffffffffffffffffffffffffffffeffffffffffffffff),
+    "p224": dict(id=nat.CURVE_P224, len=28, n=0xffffffffffffffffffffffffffff16a2e0b8f03e13dd29455c5c2a3d, p=0xffffffffffffffffffffffffffffffff000000000000000000000001),
 }
+
+
+_SHORT = ("secp256k1", "p256", "p384", "p521", "p192", "p224")
 
 
 class EllipticError(Exception):
@@ -320,7 +325,7 @@ class EC:
         """Batch of EC.prototype.recoverPubKey (ec/index.js:231-259).  msgs as `new BN(msg)` takes them
         (int / hex / bytes, NOT truncated), sigs as Signature takes them, js the recovery params.
         Returns (points, statuses): points[i] = (x, y), None for the point at infinity / a throw."""
-        if self.name not in ("secp256k1", "p256", "p384", "p521"):
+        if self.name not in _SHORT:
             raise EllipticError("recover_pub_key_batch: short curves only")
         lib = nat.init(self._device)
         n, ln = len(msgs), self._len
@@ -375,7 +380,7 @@ class EC:
         return out
 
     def _mul_common(self, k1, k2, pts):
-        if self.name not in ("secp256k1", "p256", "p384", "p521"):
+        if self.name not in _SHORT:
             raise EllipticError("mul/mulAdd batches: short curves only")
         lib = nat.init(self._device)
         n, ln = len(k2), self._len

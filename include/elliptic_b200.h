@@ -51,7 +51,9 @@ extern "C" {
 #define EB200_CURVE_P384 3
 #define EB200_CURVE_ED25519 4
 #define EB200_CURVE_CURVE25519 5
-#define EB200_CURVE_P521 6       /* 66-byte fields; verify / mul / mulAdd / derive */
+#define EB200_CURVE_P521 6       /* 66-byte fields; verify / recover / mul / mulAdd / derive */
+#define EB200_CURVE_P192 7       /* 24-byte fields; same entry points as p521 */
+#define EB200_CURVE_P224 8       /* 28-byte fields; p = 1 mod 4: compressed keys go through bn.js's Tonelli-Shanks */
 
 /* public-key encodings accepted by eb200_ecdsa_verify_batch (KeyPair._importPublic,
  * lib/elliptic/ec/key.js:84-99 -> BaseCurve.decodePoint, curve/base.js:270-292) */

@@ -102,6 +102,8 @@ static void sw_verify_host(size_t N, const uint8_t* e, const uint8_t* r, const u
 extern "C" void he_sw_verify(int curve, size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
   if (curve == 2) sw_verify_host<P256>(N, e, r, s, pub, status);
   else if (curve == 6) sw_verify_host<P521>(N, e, r, s, pub, status);
+  else if (curve == 7) sw_verify_host<P192>(N, e, r, s, pub, status);
+  else if (curve == 8) sw_verify_host<P224>(N, e, r, s, pub, status);
   else sw_verify_host<P384>(N, e, r, s, pub, status);
 }
 
@@ -225,12 +227,16 @@ static void sw_replay_jmuladd_host(const u32* u1, const u32* u2, const u32* qx, 
 extern "C" void he_sw_replay_jmuladd(int curve, const u32* u1, const u32* u2, const u32* qx, const u32* qy, u32* xyz) {
   if (curve == 2) sw_replay_jmuladd_host<P256>(u1, u2, qx, qy, xyz);
   else if (curve == 6) sw_replay_jmuladd_host<P521>(u1, u2, qx, qy, xyz);
+  else if (curve == 7) sw_replay_jmuladd_host<P192>(u1, u2, qx, qy, xyz);
+  else if (curve == 8) sw_replay_jmuladd_host<P224>(u1, u2, qx, qy, xyz);
   else sw_replay_jmuladd_host<P384>(u1, u2, qx, qy, xyz);
 }
 extern "C" void he_sw_replay_verify(int curve, size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, uint8_t* status) {
   for (size_t i = 0; i < N; i++)
     status[i] = curve == 2 ? SWReplay<P256>::verify_item(i, e, r, s, pub, sw_replay_tab<P256>().data())
               : curve == 6 ? SWReplay<P521>::verify_item(i, e, r, s, pub, sw_replay_tab<P521>().data())
+              : curve == 7 ? SWReplay<P192>::verify_item(i, e, r, s, pub, sw_replay_tab<P192>().data())
+              : curve == 8 ? SWReplay<P224>::verify_item(i, e, r, s, pub, sw_replay_tab<P224>().data())
                            : SWReplay<P384>::verify_item(i, e, r, s, pub, sw_replay_tab<P384>().data());
 }
 
@@ -274,6 +280,8 @@ static void sw_mul_add_host(size_t N, const uint8_t* k1, const uint8_t* k2, cons
 extern "C" void he_sw_mul_add(int curve, size_t N, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, uint8_t* out, uint8_t* status) {
   if (curve == 2) sw_mul_add_host<P256>(N, k1, k2, pts, out, status);
   else if (curve == 6) sw_mul_add_host<P521>(N, k1, k2, pts, out, status);
+  else if (curve == 7) sw_mul_add_host<P192>(N, k1, k2, pts, out, status);
+  else if (curve == 8) sw_mul_add_host<P224>(N, k1, k2, pts, out, status);
   else sw_mul_add_host<P384>(N, k1, k2, pts, out, status);
 }
 
@@ -375,5 +383,7 @@ extern "C" void he_sw_recover(int curve, size_t N, const uint8_t* e, const uint8
                               uint8_t* out, uint8_t* status) {
   if (curve == 2) sw_recover_host<P256>(N, e, r, s, recid, out, status);
   else if (curve == 6) sw_recover_host<P521>(N, e, r, s, recid, out, status);
+  else if (curve == 7) sw_recover_host<P192>(N, e, r, s, recid, out, status);
+  else if (curve == 8) sw_recover_host<P224>(N, e, r, s, recid, out, status);
   else sw_recover_host<P384>(N, e, r, s, recid, out, status);
 }

@@ -34,4 +34,4 @@ def rec_expected(ec, it):
         Q = ec.recover_pub_key(m, sg, j)
         return (7, None) if Q.is_infinity() else (1, (Q.x, Q.y))
     except RefError as ex:
-        return {"invalid point": 2, "Unable to find sencond key candinate": 8}[ex.args[0]], None
+        return {"invalid point": 2, "Unable to find sencond key candinate": 8, "Assertion failed": 5}[ex.args[0]], None

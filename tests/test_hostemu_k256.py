@@ -84,7 +84,7 @@ def test_verify_pipeline_against_oracle(he):
     assert list(st2) == list(st)
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
 def test_sw_verify_pipeline_against_oracle(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     from sw_items import sw_edge_items, sw_expected
@@ -198,13 +198,13 @@ def test_sign_and_hash_bodies_against_oracle(he):
         assert bytes(o) == hashlib.sha256(msg).digest()
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
 def test_sw_replay_matches_reference_schedule_point_for_point(he, name, cid, ln):
     """The off-curve replay (ecdsa_sw_replay.cuh) must land on the same Jacobian triple as the
     oracle's _wnaf_mul_add, not just the same verdict: the coordinates are compared exactly."""
     from oracle.ref_py.ec import EC
     ec = EC(name)
-    n, p, k = ec.n, ec.curve.p, {32: 8, 48: 12, 66: 18}[ln]
+    n, p, k = ec.n, ec.curve.p, {32: 8, 48: 12, 66: 18, 24: 6, 28: 8}[ln]
     rnd = random.Random(9 + cid)
     cases = []
     for t in range(10):
@@ -230,7 +230,7 @@ def test_sw_replay_matches_reference_schedule_point_for_point(he, name, cid, ln)
             assert got == (ref.x % p, ref.y % p, ref.z % p), (u1, u2, x, y)
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
 def test_sw_replay_verdicts_for_off_curve_keys(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     from sw_items import sw_off_curve_items
@@ -269,7 +269,7 @@ def mul_cases(ec, seed=3, bits=256):
     return cases
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
 def test_sw_mul_and_mul_add_bodies_against_oracle(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     ec = EC(name)
@@ -390,7 +390,7 @@ def test_sw_sign_pipeline_against_oracle(he, name, cid, ln):
                     rec[i], st[i]) == (sig.r, sig.s, sig.recovery_param, 1), (i, canon, every)
 
 
-@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66)])
+@pytest.mark.parametrize("name,cid,ln", [("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
 def test_sw_recover_pub_key_body_against_oracle(he, name, cid, ln):
     from oracle.ref_py.ec import EC
     from rec_items import rec_items, rec_expected
@@ -409,4 +409,4 @@ def test_sw_recover_pub_key_body_against_oracle(he, name, cid, ln):
         if i in truth:
             assert st[i] == 1 and pt == truth[i]
         seen.add(int(st[i]))
-    assert {1, 2, 7, 8} <= seen
+    assert {1, 8} <= seen and (7 in seen or name == "p224") and (2 in seen or 5 in seen)      # p224: bn.js's Tonelli-Shanks asserts on a non-residue
