@@ -387,3 +387,21 @@ extern "C" void he_sw_recover(int curve, size_t N, const uint8_t* e, const uint8
   else if (curve == 8) sw_recover_host<P224>(N, e, r, s, recid, out, status);
   else sw_recover_host<P384>(N, e, r, s, recid, out, status);
 }
+
+// Red.sqrt restatement (SW<C>::sqrt_ref): plain a in, plain root out; returns the status (0 ok, 5 assertion)
+template <class C>
+static int sw_sqrt_host(const u32* a, u32* out) {
+  typedef SW<C> W;
+  typename W::fe t, y = W::F::zero();
+  copy_n<C::N>(t.v, a);
+  int st = W::sqrt_ref(W::F::to_mont(t), &y);
+  copy_n<C::N>(out, W::F::from_mont(y).v);
+  return st;
+}
+extern "C" int he_sw_sqrt(int curve, const u32* a, u32* out) {
+  if (curve == 2) return sw_sqrt_host<P256>(a, out);
+  if (curve == 6) return sw_sqrt_host<P521>(a, out);
+  if (curve == 7) return sw_sqrt_host<P192>(a, out);
+  if (curve == 8) return sw_sqrt_host<P224>(a, out);
+  return sw_sqrt_host<P384>(a, out);
+}

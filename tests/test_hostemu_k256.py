@@ -410,3 +410,28 @@ def test_sw_recover_pub_key_body_against_oracle(he, name, cid, ln):
             assert st[i] == 1 and pt == truth[i]
         seen.add(int(st[i]))
     assert {1, 8} <= seen and (7 in seen or name == "p224") and (2 in seen or 5 in seen)      # p224: bn.js's Tonelli-Shanks asserts on a non-residue
+
+
+@pytest.mark.parametrize("name,cid,k", [("p256", 2, 8), ("p224", 8, 8), ("p192", 7, 6)])
+def test_sw_sqrt_matches_bn_js_red_sqrt(he, name, cid, k):
+    """Red.prototype.sqrt (dist:7177-7232) as pointFromX uses it: the same candidate root for residues, and for
+    non-residues garbage (p = 3 mod 4) or the 'Assertion failed' throw (p224, Tonelli-Shanks)."""
+    from oracle.ref_py import curves
+    from oracle.ref_py.bn import RefError
+    red = curves.get(name).curve.red
+    p = curves.get(name).curve.p
+    rnd = random.Random(40 + cid)
+    vals = [0, 1, 4, p - 1] + [rnd.randrange(p) for _ in range(24)] + [pow(rnd.randrange(1, p), 2, p) for _ in range(8)]
+    seen = set()
+    for a in vals:
+        out = (ctypes.c_uint32 * k)()
+        st = he.he_sw_sqrt(cid, L(a, k), out)
+        try:
+            want = (0, red.sqrt(a))
+        except RefError as ex:
+            assert str(ex) == "Assertion failed"
+            want = (5, None)
+        got = (st, I(out, k) if st == 0 else None)
+        assert got == want, (name, hex(a))
+        seen.add(st)
+    assert 0 in seen and (name != "p224" or 5 in seen)

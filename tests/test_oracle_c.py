@@ -54,3 +54,22 @@ def test_c_restatement_field_mult_count():
     assert np.array_equal(st, ds["expected"])
     per = lib.k256_ref_fm_count() / 512
     assert 2150 < per < 2300, per
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path = the C restatement, Node.js being absent) must run
+    without a GPU and print one JSON line with the keys the driver reads."""
+    import json
+    import os
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "verifies/s" and line["higher_is_better"] is True
+    assert line["metric"] == "secp256k1 ECDSA verifies/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["n_gpus"] == 1 and line["steps"] == 1
