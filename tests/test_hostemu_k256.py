@@ -435,3 +435,35 @@ def test_sw_sqrt_matches_bn_js_red_sqrt(he, name, cid, k):
         assert got == want, (name, hex(a))
         seen.add(st)
     assert 0 in seen and (name != "p224" or 5 in seen)
+
+
+def test_der_import_fuzz_with_hypothesis(he):
+    """Structured fuzzing of the DER importer against the oracle: arbitrary byte strings, and valid encodings with a
+    slice replaced, must be accepted / rejected identically and yield the same integers."""
+    from hypothesis import given, settings, strategies as st
+    from oracle.ref_py.signature import Signature
+
+    def check(der):
+        want = ref_der(der)
+        r, s = (ctypes.c_uint8 * 32)(), (ctypes.c_uint8 * 32)()
+        ok = he.he_der_import(der, ctypes.c_size_t(len(der)), ctypes.c_size_t(32), r, s)
+        assert bool(ok) == (want is not None), der.hex()
+        if want:
+            fit = lambda v: v if v < 2 ** 256 else 0
+            assert (int.from_bytes(bytes(r), "big"), int.from_bytes(bytes(s), "big")) == (fit(want[0]), fit(want[1])), der.hex()
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.binary(max_size=80))
+    def arbitrary(der):
+        check(der)
+
+    @settings(max_examples=400, deadline=None)
+    @given(st.integers(1, 2 ** 264), st.integers(1, 2 ** 256), st.integers(0, 79), st.binary(max_size=4))
+    def spliced(r, s, pos, patch):
+        der = bytearray(Signature({"r": r, "s": s}).to_der())
+        pos %= len(der)
+        der[pos:pos + len(patch)] = patch
+        check(bytes(der))
+
+    arbitrary()
+    spliced()

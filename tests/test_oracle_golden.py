@@ -197,3 +197,29 @@ def test_ed25519_all_1024_reference_vectors_when_reference_present():
     for ln in lines[::8]:
         sk_pk, pk, msg, sig_msg, _ = ln.split(":")
         assert ed.verify(msg, sig_msg[:128], pk) is True
+
+
+@pytest.mark.parametrize("name", ["p192", "p224", "p256", "p384", "p521", "secp256k1"])
+def test_oracle_accepts_openssl_signatures_on_every_short_preset(name):
+    """Independent pin for the presets without verify vectors in the reference: signatures made by OpenSSL
+    (`cryptography`) over random digests verify under the oracle, and stop verifying when the digest changes."""
+    import random
+    from cryptography.hazmat.primitives.asymmetric import ec as cec, utils as cutils
+    from cryptography.hazmat.primitives import hashes
+    from oracle.ref_py.ec import EC
+    curve = {"p192": cec.SECP192R1(), "p224": cec.SECP224R1(), "p256": cec.SECP256R1(), "p384": cec.SECP384R1(),
+             "p521": cec.SECP521R1(), "secp256k1": cec.SECP256K1()}[name]
+    ec = EC(name)
+    rnd = random.Random(7)
+    try:
+        key = cec.generate_private_key(curve)
+    except Exception as ex:                       # an OpenSSL build without the small curves
+        pytest.skip(str(ex))
+    pub = key.public_key().public_numbers()
+    for _ in range(4):
+        dg = rnd.randbytes(32)
+        r, s = cutils.decode_dss_signature(key.sign(dg, cec.ECDSA(cutils.Prehashed(hashes.SHA256()))))
+        # OpenSSL truncates the digest to the bit length of n exactly as _truncateToN does for a byte array
+        assert ec.verify(dg, {"r": r, "s": s}, {"x": pub.x, "y": pub.y}) is True
+        bad = bytearray(dg); bad[0] ^= 0x40
+        assert ec.verify(bytes(bad), {"r": r, "s": s}, {"x": pub.x, "y": pub.y}) is False
