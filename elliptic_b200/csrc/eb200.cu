@@ -1082,14 +1082,14 @@ extern "C" {
 int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t* priv, uint32_t flags,
                            uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status) {
   if (!g.ready) return EB200_ERR_NOT_INIT;
-  if (curve != EB200_CURVE_SECP256K1 && curve != EB200_CURVE_P256 && curve != EB200_CURVE_P384) return EB200_ERR_UNSUPPORTED;
+  if (!curve_ok(curve)) return EB200_ERR_UNSUPPORTED;
   if (n == 0) return EB200_OK;
   if (!e || !priv || !out_r || !out_s || !out_recid || !status) return EB200_ERR_ARG;
   std::lock_guard<std::mutex> lk(g_mu);
   CK(cudaSetDevice(g.device));
   int rc = ensure_table(curve);
   if (rc) return rc;
-  const size_t len = curve_len(curve), limbs = len / 4;
+  const size_t len = curve_len(curve), limbs = fe_len(curve) / 4;
   if ((rc = grow(&g.d_in, &g.d_in_cap, n * (4 * len + 1) + 256))) return rc;
   if ((rc = grow(&g.d_status, &g.d_status_cap, n))) return rc;
   const size_t ws_bytes = align256(4 * limbs * 4 * n);                 // X, Y, Z, k
@@ -1106,6 +1106,12 @@ int eb200_ecdsa_sign_batch(int curve, size_t n, const uint8_t* e, const uint8_t*
     if ((rc = sw_sign_launch<SWSign<P256, Sha256W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
   } else if (curve == EB200_CURVE_P384) {
     if ((rc = sw_sign_launch<SWSign<P384, Sha384W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
+  } else if (curve == EB200_CURVE_P521) {     // curves.js:124, 50, 65: sha512, sha256, sha256
+    if ((rc = sw_sign_launch<SWSign<P521, Sha512W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
+  } else if (curve == EB200_CURVE_P192) {
+    if ((rc = sw_sign_launch<SWSign<P192, Sha256W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
+  } else if (curve == EB200_CURVE_P224) {
+    if ((rc = sw_sign_launch<SWSign<P224, Sha256W>>(curve, n, d_e, d_k, canonical, d_sws, d_scr, d_r, d_s, d_id, st))) return rc;
   } else {
     unsigned nb = (unsigned)((n + 127) / 128);
     size_t T = (n + PREP_BATCH - 1) / PREP_BATCH;

@@ -10,6 +10,55 @@
 
 namespace eb {
 
+// Nonce source: HMAC-DRBG seeded with (private key, message), yielding candidate k's as little-endian limbs.
+// WORDS = true: key, message and digest have the same length (p256 / SHA-256, p384 / SHA-384) -> the register-only
+// generator; false: any lengths (p192, p224, p521) -> the byte-stream generator, plus _truncateToN(k, true).
+template <class C, class H, bool WORDS>
+struct SignDrbg;
+
+template <class C, class H>
+struct SignDrbg<C, H, true> {
+  typedef typename H::W HW;
+  static constexpr int N = C::N;
+  HmacDrbgW<H> g;
+  EB_HD void init(const uint8_t* priv, const uint8_t* msg) {
+    constexpr int B = H::WB / 8;
+    HW dw[H::D], ew[H::D];
+    for (int i = 0; i < H::D; i++) {
+      HW a = 0, b = 0;
+      for (int k = 0; k < B; k++) { a = (a << 8) | priv[B * i + k]; b = (b << 8) | msg[B * i + k]; }
+      dw[i] = a; ew[i] = b;
+    }
+    g.init(dw, ew);
+  }
+  EB_HD void next_k(u32* k) {
+    constexpr int B = H::WB / 32;                // 32-bit limbs per hash word
+    HW kw[H::D];
+    g.generate(kw);
+    for (int i = 0; i < H::D; i++)
+      for (int j = 0; j < B; j++) k[N - 1 - (B * i + j)] = (u32)(kw[i] >> (H::WB - 32 * (j + 1)));
+  }
+};
+
+template <class C, class H>
+struct SignDrbg<C, H, false> {
+  static constexpr int N = C::N;
+  HmacDrbgB<H> g;
+  EB_HD void init(const uint8_t* priv, const uint8_t* msg) { g.init(priv, C::LEN, msg, C::LEN); }
+  EB_HD void next_k(u32* k) {
+    uint8_t kb[C::LEN];
+    g.generate(kb, C::LEN);                                  // drbg.generate(n.byteLength())
+    load_be_len<N>(k, kb, C::LEN);
+    // _truncateToN(k, true) (ec/index.js:81-108, BN input): the shift is taken from the VALUE's byte length
+    int top = 0;
+    while (top < C::LEN && kb[top] == 0) top++;
+    int delta = 8 * (C::LEN - top) - C::BITS;
+    if (delta > 0) {
+      for (int w = 0; w < N; w++) k[w] = (k[w] >> delta) | ((w + 1 < N ? k[w + 1] : 0u) << (32 - delta));
+    }
+  }
+};
+
 template <class C, class H>
 struct SWSign {
   typedef SW<C> W;
@@ -19,29 +68,13 @@ struct SWSign {
   typedef typename S::fe sc;
   typedef typename W::jac jac;
   typedef typename W::aff aff;
-  typedef HmacDrbgW<H> Drbg;
-  typedef typename H::W HW;
+  static constexpr bool WORDS = (C::LEN == 4 * C::N) && (C::LEN == H::D * H::WB / 8);
+  typedef SignDrbg<C, H, WORDS> Drbg;
   static constexpr int N = C::N;
   static constexpr int WS_WORDS = 4 * N;        // X, Y, Z, k  (word-major SoA)
   static constexpr int SCRATCH_WORDS = 2 * N;   // prefix products of Z and k
   static constexpr int BATCH = 16;
-  static_assert(C::LEN == 4 * N && C::LEN == Drbg::DBYTES, "key, message and digest must have the same length");
 
-  // LEN big-endian bytes -> big-endian hash words
-  static EB_HD void be_words(HW* w, const uint8_t* p) {
-    constexpr int B = H::WB / 8;
-    for (int i = 0; i < H::D; i++) {
-      HW v = 0;
-      for (int k = 0; k < B; k++) v = (v << 8) | p[B * i + k];
-      w[i] = v;
-    }
-  }
-  // big-endian hash words -> little-endian 32-bit limbs
-  static EB_HD void words_to_limbs(u32* k, const HW* w) {
-    constexpr int B = H::WB / 32;                // 32-bit limbs per hash word
-    for (int i = 0; i < H::D; i++)
-      for (int j = 0; j < B; j++) k[N - 1 - (B * i + j)] = (u32)(w[i] >> (H::WB - 32 * (j + 1)));
-  }
   // ec/index.js:158-159
   static EB_HD bool k_in_range(const u32* k) {
     u32 nmod[N], ns1[N], one[N];
@@ -80,14 +113,10 @@ struct SWSign {
 
   static EB_HD void nonce_item(size_t i, size_t cnt, const uint8_t* e, const uint8_t* priv, const u32* gtab, u32* ws,
                                uint8_t* status) {
-    HW dw[H::D], ew[H::D], kw[H::D];
-    be_words(dw, priv + C::LEN * i);
-    be_words(ew, e + C::LEN * i);
     Drbg g;
-    g.init(dw, ew);
-    g.generate(kw);
+    g.init(priv + C::LEN * i, e + C::LEN * i);
     u32 k[N];
-    words_to_limbs(k, kw);
+    g.next_k(k);
     bool ok = k_in_range(k);
     jac acc = W::infinity();
     if (ok) acc = mul_g_jac(k, gtab);
@@ -175,15 +204,11 @@ struct SWSign {
   // the literal loop of ec/index.js:153-185 for one flagged item
   static EB_HD uint8_t slow_item(size_t i, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,
                                  uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
-    HW dw[H::D], ew[H::D], kw[H::D];
-    be_words(dw, priv + C::LEN * i);
-    be_words(ew, e + C::LEN * i);
     Drbg g;
-    g.init(dw, ew);
+    g.init(priv + C::LEN * i, e + C::LEN * i);
     for (int iter = 0; iter < 128; iter++) {
-      g.generate(kw);
       u32 k[N];
-      words_to_limbs(k, kw);
+      g.next_k(k);
       if (!k_in_range(k)) continue;
       aff kp = W::to_aff(mul_g_jac(k, gtab));
       sc km;

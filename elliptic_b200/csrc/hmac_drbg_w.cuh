@@ -187,3 +187,117 @@ struct HmacDrbgW {
 };
 
 }  // namespace eb
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same generator for key / message lengths that are not one digest long (p192 and p224 with SHA-256, p521 with
+// SHA-512; curves.js:43-71,109-134): messages are assembled as bytes and hashed block by block.  Not a hot path.
+namespace eb {
+
+struct Sha512W : Sha384W {
+  static constexpr int D = 8;
+  static EB_HD void iv(W* s) {
+    const W v[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                    0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+    for (int i = 0; i < 8; i++) s[i] = v[i];
+  }
+};
+
+template <class H>
+struct HashStreamW {                      // Merkle-Damgard streaming over H::compress
+  typedef typename H::W W;
+  static constexpr int WBY = H::WB / 8, BB = 16 * WBY;
+  W st[8];
+  uint8_t buf[BB];
+  int fill;
+  u64 total;
+  EB_HD void block() {
+    W w[16];
+    for (int i = 0; i < 16; i++) {
+      W v = 0;
+      for (int k = 0; k < WBY; k++) v = (v << 8) | buf[WBY * i + k];
+      w[i] = v;
+    }
+    H::compress(st, w);
+    fill = 0;
+  }
+  EB_HD void start(const W* state, u64 already) { for (int i = 0; i < 8; i++) st[i] = state[i]; fill = 0; total = already; }
+  EB_HD void absorb(const uint8_t* p, int n) {
+    total += (u64)n;
+    for (int i = 0; i < n; i++) { buf[fill++] = p[i]; if (fill == BB) block(); }
+  }
+  EB_HD void finish(uint8_t* out, int nbytes) {
+    u64 bits = total * 8;
+    buf[fill++] = 0x80;
+    if (fill > BB - 2 * WBY) { while (fill < BB) buf[fill++] = 0; block(); }
+    while (fill < BB - 8) buf[fill++] = 0;                    // the high half of a 128-bit length is zero
+    for (int k = 0; k < 8; k++) buf[BB - 8 + k] = (uint8_t)(bits >> (56 - 8 * k));
+    fill = BB;
+    block();
+    for (int i = 0; i < nbytes; i++) out[i] = (uint8_t)(st[i / WBY] >> (8 * (WBY - 1 - i % WBY)));
+  }
+};
+
+template <class H>
+struct HmacDrbgB {
+  typedef typename H::W W;
+  static constexpr int DB = H::D * H::WB / 8;                 // digest bytes
+  static constexpr int BB = 16 * H::WB / 8;
+  W kin[8], kout[8];
+  uint8_t V[DB];
+  bool first;
+
+  EB_HD void set_key(const uint8_t* key) {
+    uint8_t pad[BB];
+    HashStreamW<H> s;
+    W iv[8];
+    H::iv(iv);
+    for (int i = 0; i < BB; i++) pad[i] = (i < DB ? key[i] : 0) ^ 0x36;
+    s.start(iv, 0); s.absorb(pad, BB);
+    for (int i = 0; i < 8; i++) kin[i] = s.st[i];
+    for (int i = 0; i < BB; i++) pad[i] = (i < DB ? key[i] : 0) ^ 0x5c;
+    s.start(iv, 0); s.absorb(pad, BB);
+    for (int i = 0; i < 8; i++) kout[i] = s.st[i];
+  }
+  // HMAC(K, V || [sep] || a || b)
+  EB_HD void mac(bool with_sep, uint8_t sep, const uint8_t* a, int na, const uint8_t* b, int nb, uint8_t* out) const {
+    HashStreamW<H> s;
+    uint8_t inner[DB];
+    s.start(kin, BB);
+    s.absorb(V, DB);
+    if (with_sep) s.absorb(&sep, 1);
+    if (na) s.absorb(a, na);
+    if (nb) s.absorb(b, nb);
+    s.finish(inner, DB);
+    s.start(kout, BB);
+    s.absorb(inner, DB);
+    s.finish(out, DB);
+  }
+  EB_HD void init(const uint8_t* entropy, int ne, const uint8_t* nonce, int nn) {
+    uint8_t K[DB];
+    for (int i = 0; i < DB; i++) { K[i] = 0x00; V[i] = 0x01; }
+    set_key(K);
+    mac(true, 0x00, entropy, ne, nonce, nn, K);
+    set_key(K);
+    mac(false, 0, nullptr, 0, nullptr, 0, V);
+    mac(true, 0x01, entropy, ne, nonce, nn, K);
+    set_key(K);
+    mac(false, 0, nullptr, 0, nullptr, 0, V);
+    first = true;
+  }
+  EB_HD void generate(uint8_t* out, int len) {
+    if (!first) {
+      uint8_t K[DB];
+      mac(true, 0x00, nullptr, 0, nullptr, 0, K);
+      set_key(K);
+      mac(false, 0, nullptr, 0, nullptr, 0, V);
+    }
+    first = false;
+    int got = 0;
+    while (got < len) {
+      mac(false, 0, nullptr, 0, nullptr, 0, V);
+      for (int i = 0; i < DB && got < len; i++) out[got++] = V[i];
+    }
+  }
+};
+
+}  // namespace eb

@@ -295,8 +295,8 @@ class EC:
     def sign_batch(self, msgs, privs, canonical=False, msg_bit_length=None):
         """Batch of EC.prototype.sign (ec/index.js:110-186) with the default hash and RFC 6979 nonces
         (no `pers`, no custom `k`).  Returns (r list, s list, recoveryParam array)."""
-        if self.name not in ("secp256k1", "p256", "p384"):
-            raise EllipticError("sign_batch: secp256k1, p256 and p384 are accelerated")
+        if self.name not in _SHORT:
+            raise EllipticError("sign_batch: short curves only")
         lib = nat.init(self._device)
         n, ln = len(msgs), self._len
         e = np.zeros((n, ln), np.uint8); d = np.zeros((n, ln), np.uint8)

@@ -104,8 +104,9 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
                                  const uint8_t* d_s, const uint8_t* d_pub, uint32_t pub_fmt,
                                  uint8_t* d_status, void* d_workspace, void* stream);
 
-/* Batch of EC.prototype.sign (lib/elliptic/ec/index.js:110-186) on secp256k1, p256 (len = 32) and p384 (len = 48),
- * with the curve's default hash (sha256 / sha256 / sha384, curves.js:73-107,176-206) and no `pers` / custom `k`:
+/* Batch of EC.prototype.sign (lib/elliptic/ec/index.js:110-186) on every short preset (len = the curve's field
+ * byte length), with the curve's default hash (sha256; sha384 on p384, sha512 on p521; curves.js:43-206) and no
+ * `pers` / custom `k`:
  * the RFC 6979 nonces come from HMAC-DRBG over that hash, generated on the GPU.
  *   e    : n x len  _truncateToN(msg) (ec/index.js:127) including its final `- n`, i.e. e < n, big-endian
  *   priv : n x len  private scalars as the key pair holds them (reduced mod n at import, ec/key.js:76-82)

@@ -361,6 +361,9 @@ static void sw_sign_host(size_t N, const uint8_t* e, const uint8_t* priv, u32 ca
 extern "C" void he_sw_sign(int curve, size_t N, const uint8_t* e, const uint8_t* priv, u32 canonical, uint8_t* r, uint8_t* s,
                            uint8_t* recid, uint8_t* status, int force_slow_every) {
   if (curve == 2) sw_sign_host<SWSign<P256, Sha256W>, P256>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
+  else if (curve == 6) sw_sign_host<SWSign<P521, Sha512W>, P521>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
+  else if (curve == 7) sw_sign_host<SWSign<P192, Sha256W>, P192>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
+  else if (curve == 8) sw_sign_host<SWSign<P224, Sha256W>, P224>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
   else sw_sign_host<SWSign<P384, Sha384W>, P384>(N, e, priv, canonical, r, s, recid, status, force_slow_every);
 }
 

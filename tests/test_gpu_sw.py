@@ -288,3 +288,39 @@ def test_recover_pub_key_parity(native, name):
         assert (int(st[i]), pts[i]) == rec_expected(ec, it), (i, it[3])
         if i in truth:
             assert pts[i] == truth[i]
+
+
+@pytest.mark.parametrize("name", ["p192", "p224", "p521"])
+def test_sign_batch_on_the_remaining_presets(native, name):
+    """EC.sign where key / message / digest lengths differ (p192, p224: SHA-256 with 24 / 28-byte keys; p521: SHA-512
+    with 66-byte keys and the value-dependent _truncateToN(k, true)): r, s, recoveryParam equal the oracle's, the
+    RFC 6979 vectors for the curve's default hash come out exactly, and what was signed verifies."""
+    from elliptic_b200.ec import EC as GpuEC
+    from oracle.ref_py.ec import EC
+    cid, ln = CURVES[name]
+    ec, gec = EC(name), GpuEC(name)
+    rnd = random.Random(41)
+    msgs = [rnd.randbytes(ln) for _ in range(24)] + [b"\x00" * ln, b"\xff" * ln, rnd.randbytes(20), rnd.randbytes(ln + 9)]
+    privs = [rnd.randrange(1, ec.n) for _ in msgs]
+    privs[1], privs[2] = 1, ec.n - 1
+    for canonical in (False, True):
+        r, s, rec = gec.sign_batch(msgs, privs, canonical=canonical)
+        for i, (m, d) in enumerate(zip(msgs, privs)):
+            sig = ec.sign(m, d, canonical=canonical)
+            assert (r[i], s[i], int(rec[i])) == (sig.r, sig.s, sig.recovery_param), (i, canonical)
+    pubs = [ec.g.mul(d) for d in privs]
+    st = gec.verify_batch(msgs, [{"r": a, "s": b} for a, b in zip(r, s)], [{"x": q.x, "y": q.y} for q in pubs])
+    assert bool((st == 1).all())
+    hs = {"sha256": hashlib.sha256, "sha512": hashlib.sha512}
+    default = {"p192": "sha256", "p224": "sha256", "p521": "sha512"}[name]
+    seen = 0
+    for blk in KATS["rfc6979"]:
+        if blk["curve"] != name:
+            continue
+        for c in blk["cases"]:
+            if c["hash"] != default:
+                continue
+            got = gec.sign(hs[default](c["message"].encode()).digest(), int(blk["key"], 16))
+            assert (got["r"], got["s"]) == (int(c["r"], 16), int(c["s"], 16)), c
+            seen += 1
+    assert seen >= 1
