@@ -112,7 +112,7 @@ __global__ void k_mix(u32* out, u32 seed) {
 template <int OP>
 __global__ void k_fe(u32* out, u32 seed) {
   fe a, b;
-  for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 1) + threadIdx.x; b.v[i] = seed * (i + 7) + blockIdx.x; }
+  for (int i = 0; i < 8; i++) { a.v[i] = seed * (i + 1) + threadIdx.x; b.v[i] = seed * (i + 7) + blockIdx.x + 3 * threadIdx.x; }
   for (int it = 0; it < ITERS / 4; it++) {
     if (OP == 0) { a = fe_mul(a, b); b = fe_mul(b, a); }
     if (OP == 1) { a = fe_sqr(a); b = fe_sqr(b); }
@@ -138,6 +138,62 @@ __global__ void k_ge(u32* out, u32 seed) {
   u32 s = 0;
   for (int i = 0; i < 8; i++) s ^= p.x.v[i] ^ p.y.v[i] ^ p.z.v[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- carry-free 9 x 29-bit field (fq_pm.cuh) and the group law on it (gq_k256.cuh)
+template <int OP>
+__global__ void k_fq(u32* out, u32 seed) {
+  fqk<1> a, b;
+  for (int i = 0; i < 9; i++) { a.v[i] = (seed * (i + 1) + threadIdx.x) & FQ_MASK; b.v[i] = (seed * (i + 7) + blockIdx.x + 3 * threadIdx.x) & FQ_MASK; }
+  a.v[8] &= 0xFFFFFF; b.v[8] &= 0xFFFFFF;
+  for (int it = 0; it < ITERS / 4; it++) {
+    if (OP == 0) { a = fq_mul(a, b); b = fq_mul(b, a); }
+    if (OP == 1) { a = fq_sqr(a); b = fq_sqr(b); }
+    if (OP == 2) { a = fq_weak(fq_add(a, b)); b = fq_weak(fq_sub(b, a)); }
+    if (OP == 3) { fqk<3> t = fq_sub(a, b); fqk<6> u = fq_sub(t, fq_add(a, b)); a = fq_weak(u); b = fq_weak(fq_add(b, a)); }
+  }
+  u32 s = 0;
+  for (int i = 0; i < 9; i++) s ^= a.v[i] ^ b.v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int OP>
+__global__ void k_gq(u32* out, u32 seed) {
+  gq_jac p;
+  gq_aff q;
+  for (int i = 0; i < 9; i++) {
+    p.x.v[i] = (seed * (i + 1) + threadIdx.x) & FQ_MASK; p.y.v[i] = (seed * (i + 7) + blockIdx.x) & FQ_MASK; p.z.v[i] = (seed + i) & FQ_MASK;
+    q.x.v[i] = (seed * (i + 3)) & FQ_MASK; q.y.v[i] = (seed * (i + 5) + threadIdx.x) & FQ_MASK;
+  }
+  for (int it = 0; it < ITERS / 32; it++) {
+    if (OP == 0) p = gq_dbl(p);
+    if (OP == 1) p = gq_madd(p, q);
+    if (OP == 2) p = gq_dbl_inl(p);
+    if (OP == 3) p = gq_madd_inl(p, q);
+  }
+  u32 s = 0;
+  for (int i = 0; i < 9; i++) s ^= p.x.v[i] ^ p.y.v[i] ^ p.z.v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 1:1 mix of wide MACs and funnel shifts (the carry extraction of a 29-bit-limb column sum)
+__global__ void k_mix_shf(u32* out, u32 seed) {
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x + threadIdx.x * 7;
+  u64 x[8];
+  u32 y[8];
+  for (int i = 0; i < 8; i++) { x[i] = a * (i + 1); y[i] = b + i; }
+  for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[i]) : "r"(a), "r"(b));
+        asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(y[i]) : "r"(a));
+      }
+    }
+  }
+  u64 s = 0;
+  for (int i = 0; i < 8; i++) s ^= x[i] + y[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (u32)s ^ (u32)(s >> 32);
 }
 
 template <typename K>
@@ -188,7 +244,25 @@ int main(int argc, char** argv) {
     printf(", \"fe_sqr_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) * 2 / t / 1e9);
     t = run(k_fe<2>, blocks, threads, d_out);
     printf(", \"fe_addsub_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) * 2 / t / 1e9);
+    t = run(k_fq<0>, blocks, threads, d_out);
+    printf(", \"fq_mul_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) * 2 / t / 1e9);
+    t = run(k_fq<1>, blocks, threads, d_out);
+    printf(", \"fq_sqr_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) * 2 / t / 1e9);
+    t = run(k_fq<2>, blocks, threads, d_out);
+    printf(", \"fq_addsub_weak_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) * 2 / t / 1e9);
+    t = run(k_fq<3>, blocks, threads, d_out);
+    printf(", \"fq_lazy4_weak2_%dx%d_G\": %.2f", c[0], c[1], n * (ITERS / 4) / t / 1e9);
+    t = run(k_mix_shf, blocks, threads, d_out);
+    printf(", \"mix_wide_shf_%dx%d_Tpairs\": %.3f", c[0], c[1], n * ITERS * 32 / t / 1e12);
     if (threads <= 256) {
+      t = run(k_gq<0>, blocks, threads, d_out);
+      printf(", \"gq_dbl_%dx%d_G\": %.3f", c[0], c[1], n * (ITERS / 32) / t / 1e9);
+      t = run(k_gq<1>, blocks, threads, d_out);
+      printf(", \"gq_madd_%dx%d_G\": %.3f", c[0], c[1], n * (ITERS / 32) / t / 1e9);
+      t = run(k_gq<2>, blocks, threads, d_out);
+      printf(", \"gq_dbl_inl_%dx%d_G\": %.3f", c[0], c[1], n * (ITERS / 32) / t / 1e9);
+      t = run(k_gq<3>, blocks, threads, d_out);
+      printf(", \"gq_madd_inl_%dx%d_G\": %.3f", c[0], c[1], n * (ITERS / 32) / t / 1e9);
       t = run(k_ge<0>, blocks, threads, d_out);
       printf(", \"jac_dbl_%dx%d_G\": %.3f", c[0], c[1], n * (ITERS / 32) / t / 1e9);
       t = run(k_ge<1>, blocks, threads, d_out);

@@ -23,6 +23,28 @@ def _stream(seed, tag, i):
     return int.from_bytes(hashlib.sha256(b"eb200/%08x/%s/%d" % (seed, tag, i)).digest(), "big")
 
 
+def _cpus():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _pmap(fn, items, min_items=64):
+    """map over worker processes (fork) -- the generators are pure Python and the GPU boxes have many cores."""
+    items = list(items)
+    w = min(_cpus(), 32, max(1, len(items) // 8))
+    if w <= 1 or len(items) < min_items or os.environ.get("EB200_GEN_SERIAL"):
+        return [fn(x) for x in items]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(w) as pool:
+        return pool.map(fn, items, chunksize=max(1, len(items) // (4 * w)))
+
+
+def _smul_job(args):
+    return scalar_mul_g(*args)
+
+
 def _batch_inv(vals, m):
     """Montgomery's trick; all vals non-zero mod m."""
     n = len(vals)
@@ -93,30 +115,27 @@ def gen_secp256k1_verify(n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64
     return gen_ecdsa_verify("secp256k1", n_items, seed, n_keys, corrupt_every, cache_dir)
 
 
-def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64, cache_dir=None):
-    """Returns dict of uint8 arrays e,r,s (n,len), pub (n,2*len) and expected (n,)."""
+def _ecdsa_job(args):
+    """Items of keys [j0, j1): rows j0*per_key .. min(n_items, j1*per_key) (key-major order)."""
+    curve, seed, n_items, n_keys, per_key, corrupt_every, j0, j1 = args
     P, N, _a, GX, GY, LEN = CURVES[curve]
-    n_keys = min(n_keys, n_items)
-    per_key = (n_items + n_keys - 1) // n_keys
-    if cache_dir:
-        path = os.path.join(cache_dir, "%s_%x_%d_%d_%d.npz" % (curve, seed, n_items, n_keys, corrupt_every))
-        if os.path.exists(path):
-            z = np.load(path)
-            return {k: z[k] for k in z.files}
-    d = [_stream(seed, b"key", j) % (N - 1) + 1 for j in range(n_keys)]
-    k = [_stream(seed, b"nonce", j) % (N - (per_key + 2)) + 1 for j in range(n_keys)]
+    nk = j1 - j0
+    d = [_stream(seed, b"key", j) % (N - 1) + 1 for j in range(j0, j1)]
+    k = [_stream(seed, b"nonce", j) % (N - (per_key + 2)) + 1 for j in range(j0, j1)]
     Q = [scalar_mul_g(x, curve) for x in d]
     R = [scalar_mul_g(x, curve) for x in k]
-    e_out = np.zeros((n_items, LEN), np.uint8)
-    r_out = np.zeros((n_items, LEN), np.uint8)
-    s_out = np.zeros((n_items, LEN), np.uint8)
-    pub_out = np.zeros((n_items, 2 * LEN), np.uint8)
-    expected = np.ones(n_items, np.uint8)
+    lo, hi = j0 * per_key, min(n_items, j1 * per_key)
+    rows = max(0, hi - lo)
+    e_out = np.zeros((rows, LEN), np.uint8)
+    r_out = np.zeros((rows, LEN), np.uint8)
+    s_out = np.zeros((rows, LEN), np.uint8)
+    pub_out = np.zeros((rows, 2 * LEN), np.uint8)
+    expected = np.ones(rows, np.uint8)
     pubs = [x.to_bytes(LEN, "big") + y.to_bytes(LEN, "big") for x, y in Q]
     for m in range(per_key):
         kinv = _batch_inv(k, N)
-        for j in range(n_keys):
-            i = j * per_key + m          # key-major order
+        for jj in range(nk):
+            i = (j0 + jj) * per_key + m          # key-major order
             if i >= n_items:
                 continue
             e = _stream(seed, b"msg", i)
@@ -124,10 +143,10 @@ def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every
                 e = (e << 256) | _stream(seed, b"msg2", i)
             elif LEN > 32:
                 e = (e << (8 * (LEN - 32))) | (_stream(seed, b"msg2", i) >> (8 * (64 - LEN)))
-            r = R[j][0] % N
-            s = kinv[j] * (e + r * d[j]) % N
+            r = R[jj][0] % N
+            s = kinv[jj] * (e + r * d[jj]) % N
             if r == 0 or s == 0:         # astronomically unlikely; keep the item invalid
-                expected[i] = 0
+                expected[i - lo] = 0
             if corrupt_every and i % corrupt_every == corrupt_every - 1:
                 c = _stream(seed, b"corrupt", i)
                 which, bit = c % 3, (c >> 8) % (8 * LEN - 1)
@@ -137,22 +156,37 @@ def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every
                     r ^= 1 << bit
                 else:
                     s ^= 1 << bit
-                expected[i] = 0
-            e_out[i] = np.frombuffer(e.to_bytes(LEN, "big"), np.uint8)
-            r_out[i] = np.frombuffer(r.to_bytes(LEN, "big"), np.uint8)
-            s_out[i] = np.frombuffer(s.to_bytes(LEN, "big"), np.uint8)
-            pub_out[i] = np.frombuffer(pubs[j], np.uint8)
+                expected[i - lo] = 0
+            e_out[i - lo] = np.frombuffer(e.to_bytes(LEN, "big"), np.uint8)
+            r_out[i - lo] = np.frombuffer(r.to_bytes(LEN, "big"), np.uint8)
+            s_out[i - lo] = np.frombuffer(s.to_bytes(LEN, "big"), np.uint8)
+            pub_out[i - lo] = np.frombuffer(pubs[jj], np.uint8)
         if m + 1 < per_key:
             # R_j += G (affine, batched inversion); k_j += 1
             den = [(GX - x) % P for x, _ in R]
             inv = _batch_inv(den, P)
-            for j in range(n_keys):
-                x1, y1 = R[j]
-                lam = (GY - y1) * inv[j] % P
+            for jj in range(nk):
+                x1, y1 = R[jj]
+                lam = (GY - y1) * inv[jj] % P
                 x3 = (lam * lam - x1 - GX) % P
-                R[j] = (x3, (lam * (x1 - x3) - y1) % P)
-                k[j] += 1
-    out = dict(e=e_out, r=r_out, s=s_out, pub=pub_out, expected=expected)
+                R[jj] = (x3, (lam * (x1 - x3) - y1) % P)
+                k[jj] += 1
+    return e_out, r_out, s_out, pub_out, expected
+
+
+def gen_ecdsa_verify(curve, n_items, seed=0xE1110002, n_keys=4096, corrupt_every=64, cache_dir=None):
+    """Returns dict of uint8 arrays e,r,s (n,len), pub (n,2*len) and expected (n,)."""
+    n_keys = min(n_keys, n_items)
+    per_key = (n_items + n_keys - 1) // n_keys
+    if cache_dir:
+        path = os.path.join(cache_dir, "%s_%x_%d_%d_%d.npz" % (curve, seed, n_items, n_keys, corrupt_every))
+        if os.path.exists(path):
+            z = np.load(path)
+            return {k: z[k] for k in z.files}
+    step = max(8, n_keys // 128)
+    parts = _pmap(_ecdsa_job, [(curve, seed, n_items, n_keys, per_key, corrupt_every, j0, min(n_keys, j0 + step))
+                               for j0 in range(0, n_keys, step)], min_items=2)
+    out = dict(zip(("e", "r", "s", "pub", "expected"), (np.concatenate([p[k] for p in parts]) for k in range(5))))
     if cache_dir:
         os.makedirs(cache_dir, exist_ok=True)
         np.savez(path, **out)
@@ -173,6 +207,34 @@ if __name__ == "__main__":
 N_ED = 0x1000000000000000000000000000000014DEF9DEA2F79CD65812631A5CF5D3ED
 
 
+def _ed_job(args):
+    import nacl.signing
+    seed, n_keys, corrupt_every, lo, hi = args
+    n = hi - lo
+    keys = {}
+    R = np.zeros((n, 32), np.uint8); S = np.zeros((n, 32), np.uint8); A = np.zeros((n, 32), np.uint8)
+    H = np.zeros((n, 32), np.uint8); M = np.zeros((n, 32), np.uint8)
+    expected = np.ones(n, np.uint8)
+    for i in range(lo, hi):
+        j = i % n_keys
+        if j not in keys:
+            k = nacl.signing.SigningKey(hashlib.sha256(b"eb200/%08x/edkey/%d" % (seed, j)).digest())
+            keys[j] = (k, bytes(k.verify_key))
+        key, pub = keys[j]
+        msg = hashlib.sha256(b"eb200/%08x/edmsg/%d" % (seed, i)).digest()
+        sig = key.sign(msg).signature
+        if corrupt_every and i % corrupt_every == corrupt_every - 1:
+            msg = msg[:-1] + bytes([(msg[-1] + 1) & 255])
+            expected[i - lo] = 0
+        h = int.from_bytes(hashlib.sha512(sig[:32] + pub + msg).digest(), "little") % N_ED
+        R[i - lo] = np.frombuffer(sig[:32], np.uint8)
+        S[i - lo] = np.frombuffer(sig[32:], np.uint8)
+        A[i - lo] = np.frombuffer(pub, np.uint8)
+        H[i - lo] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
+        M[i - lo] = np.frombuffer(msg, np.uint8)
+    return R, S, A, H, M, expected
+
+
 def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, cache_dir=None, with_msgs=False):
     """Signatures are produced with libsodium (PyNaCl) -- a generator, not the code under test.
     1/64 items are forged the way test/ed25519-test.js:75-77 does (last message byte + 1)."""
@@ -183,27 +245,9 @@ def gen_ed25519_verify(n_items, seed=0xE1110003, n_keys=4096, corrupt_every=64, 
             z = np.load(path)
             return {k: z[k] for k in z.files}
     n_keys = min(n_keys, n_items)
-    keys = [nacl.signing.SigningKey(hashlib.sha256(b"eb200/%08x/edkey/%d" % (seed, j)).digest()) for j in range(n_keys)]
-    pubs = [bytes(k.verify_key) for k in keys]
-    R = np.zeros((n_items, 32), np.uint8)
-    S = np.zeros((n_items, 32), np.uint8)
-    A = np.zeros((n_items, 32), np.uint8)
-    H = np.zeros((n_items, 32), np.uint8)
-    M = np.zeros((n_items, 32), np.uint8)
-    expected = np.ones(n_items, np.uint8)
-    for i in range(n_items):
-        j = i % n_keys
-        msg = hashlib.sha256(b"eb200/%08x/edmsg/%d" % (seed, i)).digest()
-        sig = keys[j].sign(msg).signature
-        if corrupt_every and i % corrupt_every == corrupt_every - 1:
-            msg = msg[:-1] + bytes([(msg[-1] + 1) & 255])
-            expected[i] = 0
-        h = int.from_bytes(hashlib.sha512(sig[:32] + pubs[j] + msg).digest(), "little") % N_ED
-        R[i] = np.frombuffer(sig[:32], np.uint8)
-        S[i] = np.frombuffer(sig[32:], np.uint8)
-        A[i] = np.frombuffer(pubs[j], np.uint8)
-        H[i] = np.frombuffer(h.to_bytes(32, "little"), np.uint8)
-        M[i] = np.frombuffer(msg, np.uint8)
+    step = max(1024, (n_items + 4 * 32 - 1) // (4 * 32))
+    parts = _pmap(_ed_job, [(seed, n_keys, corrupt_every, lo, min(n_items, lo + step)) for lo in range(0, n_items, step)], min_items=2)
+    R, S, A, H, M, expected = (np.concatenate([p[k] for p in parts]) for k in range(6))
     out = dict(R=R, S=S, A=A, h=H, msgs=M, expected=expected)
     if cache_dir:
         os.makedirs(cache_dir, exist_ok=True)

@@ -8,7 +8,7 @@ LIB = os.path.join(HERE, "libelliptic_b200.so")
 SRC = [os.path.join(HERE, "csrc", "eb200.cu")]
 DEPS = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))] + [
     os.path.join(HERE, "..", "include", "elliptic_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-split-compile", "0",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

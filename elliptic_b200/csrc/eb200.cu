@@ -13,7 +13,6 @@
 #include "ecdsa_sw_replay.cuh"
 #include "ecdsa_k256_sign_fast.cuh"
 #include "der_sig.cuh"
-#include "ecdsa_k256_smem.cuh"
 #include "ecdsa_sw_sign.cuh"
 
 // Calls F(curve-parameter type) for the non-GLV short curve `curve`.
@@ -58,12 +57,7 @@ k256_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __r
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   if (pre && pre[i]) { status[i] = pre[i]; return; }   // the reference throws while importing the key
-#if defined(EB_VERIFY_SMEM) && EB_VERIFY_SMEM
-  __shared__ u32 sm_acc[SM_WORDS * EB_VERIFY_BLOCK];   // accumulator + shared Z per thread, word-major
-  status[i] = verify_item_sm<EB_VERIFY_BLOCK>(i, N, pub, r, ws, gtab, qtab, sm_acc + threadIdx.x);
-#else
   status[i] = verify_item(i, N, pub, r, ws, gtab, qtab);
-#endif
 }
 
 __global__ void __launch_bounds__(128) k256_prep_recover_kernel(size_t N, const uint8_t* __restrict__ e,

@@ -25,6 +25,10 @@
 #pragma once
 #include "ge_k256.cuh"
 #include "sc_k256.cuh"
+#ifndef EB_K256_FQ
+#define EB_K256_FQ 0      // 1 = hot double/add loops on the carry-free 9 x 29-bit field (fq_pm.cuh / gq_k256.cuh); measured slower on B200 (profiles/r02_imad_peak.json), kept as a build option
+#endif
+#include "gq_k256.cuh"
 
 namespace eb {
 
@@ -41,7 +45,11 @@ constexpr int PREP_WORDS = 19;
 constexpr u32 FL_INVALID = 1, FL_NEGG = 2, FL_NEG1 = 4, FL_NEG2 = 8, FL_NOG = 16;
 constexpr int PREP_BATCH = 16;          // items per thread in the batched inversion
 constexpr int QTAB_ENTRIES = 8;         // odd multiples 1,3,..,15
+#if EB_K256_FQ
+constexpr int QTAB_WORDS = QTABQ_WORDS;        // per item: (x, y, beta*x) x 8, 9 limbs padded to 12 words each
+#else
 constexpr int QTAB_WORDS = QTAB_ENTRIES * 24;  // per item: (x, y, beta*x) x 8
+#endif
 #ifndef EB_GW
 #define EB_GW 20                         // fixed-base window width in bits (r01 sweeps: 8/11/13/16 -> 25.7/24.6/24.1/23.7 ms, then 16/20/22/24 -> 22.7/22.3/22.2/22.1 ms; 20 = 13 windows, 436 MB)
 #endif
@@ -232,6 +240,98 @@ EB_HD void prep_scalars_item(size_t i, size_t N, const uint8_t* k1, const uint8_
 EB_HD void store_fe(u32* dst, const fe& a) { for (int i = 0; i < 8; i++) dst[i] = a.v[i]; }
 EB_HD fe load_fe(const u32* src) { fe a; for (int i = 0; i < 8; i++) a.v[i] = src[i]; return a; }
 
+#if EB_K256_FQ
+// u1*G + u2*Q for an ON-CURVE Q, scalars as prepared by prep_thread in ws.  Jacobian result.
+// Carry-free field version: the whole double/add schedule runs on 9 x 29-bit lazy limbs (gq_k256.cuh);
+// the packed 8 x 32 form only appears at the two ends (Q in, the fixed-base table entries, R out).
+EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32* ws, const u32* gtab, u32* qtab) {
+  // ---- per-item table: (2k+1)*Q, k = 0..7, as affine points on an isomorphic
+  // curve y^2 = x^3 + 7*Zg^6 (the a = 0 formulas never use b), Zg = zglobal.
+  u32* tab = qtab + (size_t)i * QTAB_WORDS;
+  fqk<1> zglobal;
+  {
+    gq_jac Qj; Qj.x = fqk_from_fe(Q.x); Qj.y = fqk_from_fe(Q.y); Qj.z = fqk_one();
+    gq_jac D = gq_dbl(Qj);                   // 2Q, finite for an on-curve Q
+    fqk<1> C2 = fq_sqr(D.z);
+    fqk<1> C3 = fq_mul(C2, D.z);
+    gq_jac P;                                // 2Q is affine on the curve scaled by C = D.z
+    P.x = fq_mul(Qj.x, C2);
+    P.y = fq_mul(Qj.y, C3);
+    P.z = fqk_one();
+    fq_store12(tab + 0, P.x); fq_store12(tab + FQ_PAD, P.y);
+    for (int k = 1; k < QTAB_ENTRIES; k++) {
+      gq_madd_out o = gq_madd_h(P, D.x, D.y);
+      P = o.r;
+      u32* e = tab + QTABQ_ENTRY_WORDS * k;
+      fq_store12(e, P.x); fq_store12(e + FQ_PAD, P.y);
+      fq_store12(e + 2 * FQ_PAD, o.h);       // Z_k / Z_{k-1}, consumed below
+    }
+    zglobal = fq_mul(P.z, D.z);
+    // rescale every entry to Z = Z_7 and append beta*x
+    const fqk<1> beta = fqk_from_fe(fe_beta());
+    fqk<1> zs = fqk_one();
+    for (int k = QTAB_ENTRIES - 1; k >= 0; k--) {
+      u32* e = tab + QTABQ_ENTRY_WORDS * k;
+      fqk<1> X = fq_load12(e), Y = fq_load12(e + FQ_PAD);
+      fqk<1> hk = fqk_one();
+      if (k > 0) hk = fq_load12(e + 2 * FQ_PAD);
+      if (k < QTAB_ENTRIES - 1) {
+        fqk<1> zs2 = fq_sqr(zs);
+        fqk<1> zs3 = fq_mul(zs2, zs);
+        X = fq_mul(X, zs2);
+        Y = fq_mul(Y, zs3);
+        fq_store12(e, X); fq_store12(e + FQ_PAD, Y);
+      }
+      fq_store12(e + 2 * FQ_PAD, fq_mul(X, beta));
+      zs = fq_mul(zs, hk);
+    }
+  }
+
+  // ---- u2*Q = k1*Q + k2*(lambda*Q): 33 windows of 4 bits, regular signed-odd digits
+  gq_jac acc;
+  acc.x = fqk_one(); acc.y = fqk_one(); acc.z = fqk_zero();
+  for (int w = 32; w >= 0; w--) {
+    if (w != 32)
+      for (int d = 0; d < 4; d++) acc = gq_dbl(acc);    // (the top window starts from its first table entry)
+    for (int h = 0; h < 2; h++) {
+      u32 word = ws[(size_t)((h ? 13 : 8) + (w >> 3)) * N + i];
+      u32 nib = (word >> (4 * (w & 7))) & 15;
+      bool dneg = (w != 32) && (nib < 8);
+      u32 idx = (w == 32) ? (nib & 7) : (dneg ? 7 - nib : nib - 8);
+      bool neg = dneg != (((flags & (h ? FL_NEG2 : FL_NEG1)) != 0));
+      const u32* e = tab + QTABQ_ENTRY_WORDS * idx;
+      gq_aff P;
+      P.x = fq_load12(e + (h ? 2 * FQ_PAD : 0));
+      P.y = fq_cneg(fq_load12(e + FQ_PAD), neg);
+      if (w == 32 && h == 0) acc = gq_from_aff(P);
+      else acc = gq_madd(acc, P);
+    }
+  }
+  // back to the real curve: Z *= Zg
+  acc.z = fq_mul(acc.z, zglobal);
+
+  // ---- u1*G from the fixed table: GTAB_WINDOWS windows of GTAB_W bits, regular signed-odd digits
+  if (!(flags & FL_NOG)) {                    // Point.mul: no base-point term (uniform across a batch)
+    for (int j = 0; j < GTAB_WINDOWS; j++) {
+      const int pos = GTAB_W * j;
+      u32 lo = ws[(size_t)(pos >> 5) * N + i];
+      u32 hi = ((pos >> 5) < 7) ? ws[(size_t)((pos >> 5) + 1) * N + i] : 0u;
+      u64 both = ((u64)hi << 32) | lo;
+      u32 chunk = (u32)(both >> (pos & 31)) & ((1u << GTAB_W) - 1);
+      const u32 half = 1u << (GTAB_W - 1);
+      bool dneg = (j != GTAB_WINDOWS - 1) && (chunk < half);
+      u32 idx = (j == GTAB_WINDOWS - 1) ? (chunk & (half - 1)) : (dneg ? half - 1 - chunk : chunk - half);
+      bool neg = dneg != ((flags & FL_NEGG) != 0);
+      const u32* ent = gtab + ((size_t)j * GTAB_ENTRIES + idx) * 16;
+      gq_aff P;
+      P.x = fqk_from_fe(load_fe(ent));
+      P.y = fq_cneg(fqk_from_fe(load_fe(ent + 8)), neg);
+      acc = gq_madd(acc, P);
+    }
+  }
+  return gq_to_jac(acc);
+}
+#else
 // u1*G + u2*Q for an ON-CURVE Q, scalars as prepared by prep_thread in ws.  Jacobian result.
 EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32* ws, const u32* gtab, u32* qtab) {
   // ---- per-item table: (2k+1)*Q, k = 0..7, as affine points on an isomorphic
@@ -316,6 +416,8 @@ EB_HD ge_jac k256_dsm(size_t i, size_t N, const ge_aff& Q, u32 flags, const u32*
   }
   return acc;
 }
+
+#endif  // EB_K256_FQ
 
 EB_HD uint8_t verify_item(size_t i, size_t N, const uint8_t* pub, const uint8_t* r,
                           const u32* ws, const u32* gtab, u32* qtab) {

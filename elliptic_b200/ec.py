@@ -440,6 +440,22 @@ class EC:
         vals = [int.from_bytes(out[i].tobytes(), "big") if st[i] == nat.ST_TRUE else None for i in range(n)]
         return vals, st
 
+    def derive_batch_packed(self, priv, pubx):
+        """Packed curve25519 ECDH: priv, pubx are (n, 32) uint8 arrays (big-endian; priv already reduced mod n as
+        _importPrivate does, ec/key.js:76-82).  Returns ((n, 32) shared x big-endian, statuses)."""
+        if self.name != "curve25519":
+            raise EllipticError("derive_batch_packed: curve25519 only (short curves: derive_batch)")
+        lib = nat.init(self._device)
+        priv = np.ascontiguousarray(priv, dtype=np.uint8)
+        pubx = np.ascontiguousarray(pubx, dtype=np.uint8)
+        n = priv.shape[0]
+        if priv.shape != (n, 32) or pubx.shape != (n, 32):
+            raise EllipticError("derive_batch_packed: (n, 32) arrays expected")
+        out = np.empty((n, 32), np.uint8)
+        st = np.empty(n, np.uint8)
+        nat.check(lib.eb200_x25519_derive_batch(n, priv.ctypes.data, pubx.ctypes.data, out.ctypes.data, st.ctypes.data))
+        return out, st
+
     def _derive_short(self, privs, pubs):
         """Short curves: pubs are the peer's points as {x, y} / (x, y) (keyFromPublic(...).getPublic())."""
         lib = nat.init(self._device)

@@ -531,11 +531,19 @@ static int verify_one(const uint8_t* e32, const uint8_t* r32, const uint8_t* s32
 }
 
 /* ---------------------------------------------------------------- batch driver */
-typedef struct { size_t lo, hi; const uint8_t *e, *r, *s, *pub; uint8_t* st; } job;
+/* Workers pull 64-item chunks from a shared counter, so one slow or shared core (the host is a
+   multi-tenant box) delays the batch by one chunk instead of by its whole static share. */
+typedef struct { size_t n; size_t* next; const uint8_t *e, *r, *s, *pub; uint8_t* st; } job;
+#define K256_CHUNK 64
 static void* worker(void* arg) {
   job* j = (job*)arg;
-  for (size_t i = j->lo; i < j->hi; i++)
-    j->st[i] = (uint8_t)verify_one(j->e + 32 * i, j->r + 32 * i, j->s + 32 * i, j->pub + 64 * i, j->pub + 64 * i + 32);
+  for (;;) {
+    size_t lo = __atomic_fetch_add(j->next, (size_t)K256_CHUNK, __ATOMIC_RELAXED);
+    if (lo >= j->n) break;
+    size_t hi = lo + K256_CHUNK < j->n ? lo + K256_CHUNK : j->n;
+    for (size_t i = lo; i < hi; i++)
+      j->st[i] = (uint8_t)verify_one(j->e + 32 * i, j->r + 32 * i, j->s + 32 * i, j->pub + 64 * i, j->pub + 64 * i + 32);
+  }
   return 0;
 }
 
@@ -544,15 +552,16 @@ int k256_ref_verify_batch(size_t n, const uint8_t* e, const uint8_t* r, const ui
                           uint8_t* status, int threads) {
   pthread_once(&g_once, init_tables);
   if (threads < 1) threads = 1;
-  if ((size_t)threads > n) threads = n ? (int)n : 1;
+  if ((size_t)threads > (n + K256_CHUNK - 1) / K256_CHUNK) threads = n ? (int)((n + K256_CHUNK - 1) / K256_CHUNK) : 1;
+  size_t next = 0;
+  job jb = {n, &next, e, r, s, pub, status};
+  if (threads == 1) { worker(&jb); return 0; }
   pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * threads);
-  job* jobs = (job*)malloc(sizeof(job) * threads);
-  for (int t = 0; t < threads; t++) {
-    jobs[t] = (job){n * t / threads, n * (t + 1) / threads, e, r, s, pub, status};
-    if (threads == 1) worker(&jobs[t]); else pthread_create(&th[t], 0, worker, &jobs[t]);
-  }
-  if (threads > 1) for (int t = 0; t < threads; t++) pthread_join(th[t], 0);
-  free(th); free(jobs);
+  int started = 0;
+  for (int t = 0; t < threads; t++) if (pthread_create(&th[t], 0, worker, &jb) == 0) th[started++] = th[t];
+  if (!started) worker(&jb);
+  for (int t = 0; t < started; t++) pthread_join(th[t], 0);
+  free(th);
   return 0;
 }
 

@@ -321,15 +321,39 @@ extern "C" int he_der_import(const uint8_t* data, size_t n, size_t len, uint8_t*
 }
 
 // ---------------------------------------------------------------------------
-// verify with the accumulator in "shared memory" (ecdsa_k256_smem.cuh), stride 1 on the host
-#include "../../elliptic_b200/csrc/ecdsa_k256_smem.cuh"
-extern "C" void he_verify_sm(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
-                             const u32* gtab, uint8_t* status) {
-  std::vector<u32> ws((size_t)PREP_WORDS * N), scratch((size_t)8 * N), qtab((size_t)QTAB_WORDS * N);
-  size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
-  for (size_t t = 0; t < T; t++) prep_thread(t, T, N, e, r, s, ws.data(), scratch.data());
-  u32 acc[SM_WORDS];
-  for (size_t i = 0; i < N; i++) status[i] = verify_item_sm<1>(i, N, pub, r, ws.data(), gtab, qtab.data(), acc);
+// carry-free 9 x 29-bit field (fq_pm.cuh): op 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 6 canon, 9 weak(7a), 10 is_zero;
+// operands/results are packed 8 x 32 words.  which: 0 = secp256k1 prime, 1 = 2^255 - 19.
+template <class P>
+static void fq_op_t(int op, const u32* a, const u32* b, u32* out) {
+  fq<P, 1> A = fq_from_words<P>(a), B = fq_from_words<P>(b), R;
+  switch (op) {
+    case 0: R = fq_mul(A, B); break;
+    case 1: R = fq_sqr(A); break;
+    case 2: R = fq_weak(fq_add(A, B)); break;
+    case 3: R = fq_weak(fq_sub(A, B)); break;
+    case 4: R = fq_weak(fq_neg(A)); break;
+    case 6: R = A; break;
+    case 9: R = fq_weak(fq_sub(fq_mul_int<3>(A), fq_mul_int<2>(B))); break;       // magnitude 3 + 2 + 1 + ... = 6
+    case 10: { bool z = fq_is_zero(fq_sub(A, B)); for (int i = 0; i < 8; i++) out[i] = 0; out[0] = z; return; }
+    case 11: R = fq_mul(fq_add(fq_add(A, A), A), fq_add(B, B)); break;            // magnitudes 3 x 2
+    case 12: R = fq_sqr(fq_add(A, B)); break;                                     // magnitude 2
+    case 13: R = fq_weak(fq_cneg(A, b[0] & 1)); break;
+    default: R = A;
+  }
+  fq_to_words<P>(out, fq_canon(R));
+}
+extern "C" void he_fq_op(int which, int op, const u32* a, const u32* b, u32* out) {
+  if (which == 0) fq_op_t<PmK256>(op, a, b, out); else fq_op_t<Pm25519>(op, a, b, out);
+}
+// group law on the carry-free field against the packed-field code: op 0 dbl, 1 madd
+extern "C" void he_gq_op(int op, const u32* jac24, const u32* aff16, u32* out24) {
+  ge_jac p; ge_aff q;
+  for (int i = 0; i < 8; i++) { p.x.v[i] = jac24[i]; p.y.v[i] = jac24[8 + i]; p.z.v[i] = jac24[16 + i]; q.x.v[i] = aff16[i]; q.y.v[i] = aff16[8 + i]; }
+  gq_jac P = gq_from_jac(p), R;
+  gq_aff Qa; Qa.x = fqk_from_fe(q.x); Qa.y = fqk_from_fe(q.y);
+  R = op == 0 ? gq_dbl(P) : gq_madd(P, Qa);
+  ge_jac r = gq_to_jac(R);
+  for (int i = 0; i < 8; i++) { out24[i] = r.x.v[i]; out24[8 + i] = r.y.v[i]; out24[16 + i] = r.z.v[i]; }
 }
 
 // ---------------------------------------------------------------------------
