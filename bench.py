@@ -63,6 +63,17 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cpu_quota():
+    """CPU bandwidth limit of this container in cores (cgroup v2 cpu.max), or None when unlimited / unknown.
+    The GPU boxes expose every host thread in the affinity mask but cap the container's CPU time, which is
+    why the all-thread rate is far below cores x per_core (r01: 143 k/s on one box, 716 k/s on another)."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        return None
+
+
 def load_peaks():
     hbm, how = 6650.0, "fallback"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -186,7 +197,8 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_per_step": sample},
         "cpu_baseline": {"value": value, "unit": "verifies/s", "cores": threads, "kind": "port",
-                         "per_core": one, "total": value,
+                         "per_core": one, "total": value, "effective_cores": value / one,
+                         "cgroup_cpu_quota_cores": cpu_quota(),
                          "sample": "%d signatures/step x %d steps of the same 2^20 workload, oracle/c/k256_ref.c (C "
                                    "restatement of the reference's GLV+JSF+wNAF algorithm; Node.js not installed); "
                                    "per_core = the same code on one thread" % (sample, args.steps)},
@@ -534,6 +546,7 @@ def run_gpu(args):
             total, one, used = cpu_rates(ds, threads)
             line["cpu_baseline"] = {
                 "value": total, "unit": "verifies/s", "cores": threads, "kind": "port", "per_core": one, "total": total,
+                "effective_cores": total / one, "cgroup_cpu_quota_cores": cpu_quota(),
                 "sample": "%d signatures of the same workload on %d threads (median of 3), 2048 on one thread; "
                           "oracle/c/k256_ref.c (C restatement of the reference algorithm, 64-bit limbs; Node.js is not "
                           "installed so the JS itself cannot run)" % (used, threads)}
@@ -552,6 +565,93 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """--single-process: ONE host process drives N GPUs through the library's own sharding
+    (eb200_init(devices[], N) + eb200_ecdsa_verify_batch over the whole N x 2^20 batch).  The per-GPU shards and
+    seeds are those of the torchrun launch; statuses come home with each device's own D2H copy (the library's
+    gather), so no NCCL communicator is involved in this mode."""
+    import torch
+    from elliptic_b200 import _native as nat
+    from elliptic_b200.ec import EC
+    N = args.gpus
+    assert torch.cuda.device_count() >= N, "not enough GPUs"
+    lib = nat.init_devices(list(range(N)))
+    n = 1 << LOG2_BATCH
+    shards = [dataset(g, N) for g in range(N)]
+    cols = ("e", "r", "s", "pub")
+    big = {k: np.concatenate([d[k] for d in shards]) for k in cols}
+    expected = np.concatenate([d["expected"] for d in shards])
+    ec = EC("secp256k1", device=0)
+    # ---- device-resident arm: each GPU holds its shard; one host thread enqueues on all of them
+    dev = [torch.device("cuda", g) for g in range(N)]
+    d = [{k: torch.from_numpy(shards[g][k]).to(dev[g]) for k in cols} for g in range(N)]
+    d_status = [torch.empty(n, dtype=torch.uint8, device=dev[g]) for g in range(N)]
+    ws_bytes = lib.eb200_ecdsa_verify_workspace_bytes(nat.CURVE_SECP256K1, n)
+    d_ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev[g]) for g in range(N)]
+    streams = [torch.cuda.current_stream(dev[g]).cuda_stream for g in range(N)]
+
+    def step():
+        for g in range(N):
+            nat.check(lib.eb200_ecdsa_verify_batch_dev(
+                nat.CURVE_SECP256K1, n, d[g]["e"].data_ptr(), d[g]["r"].data_ptr(), d[g]["s"].data_ptr(), d[g]["pub"].data_ptr(),
+                nat.PUB_XY, d_status[g].data_ptr(), d_ws[g].data_ptr(), streams[g]))
+
+    def sync():
+        for g in range(N):
+            torch.cuda.synchronize(dev[g])
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
+    sync()
+    for g in range(N):
+        assert np.array_equal(d_status[g].cpu().numpy(), shards[g]["expected"]), "GPU %d statuses differ" % g
+    sampler = ClockSampler(0)
+    sampler.start()
+    ev = []
+    for g in range(N):
+        with torch.cuda.device(dev[g]):
+            ev.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+            ev[g][0].record()
+    for _ in range(args.steps):
+        step()
+    for g in range(N):
+        with torch.cuda.device(dev[g]):
+            ev[g][1].record()
+    sync()
+    total_ms = max(ev[g][0].elapsed_time(ev[g][1]) for g in range(N))        # max over GPUs, device clocks
+    ms_per_step = total_ms / args.steps
+    value = n * N / (ms_per_step * 1e-3)
+    # ---- end-to-end arm: one host call over the whole batch, host buffers, library-internal sharding
+    def e2e(hn, steps):
+        for _ in range(2):
+            st = ec.verify_batch_packed(hn["e"], hn["r"], hn["s"], hn["pub"])
+        assert np.array_equal(st, expected)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            st = ec.verify_batch_packed(hn["e"], hn["r"], hn["s"], hn["pub"])
+        return n * N * steps / (time.perf_counter() - t0), nat.last_timing()
+    e2e_steps = max(3, min(args.steps, 10))
+    hp = {k: torch.from_numpy(big[k]).pin_memory() for k in cols}
+    e2e_value, tm = e2e({k: v.numpy() for k, v in hp.items()}, e2e_steps)
+    e2e_pageable, _ = e2e(big, e2e_steps)
+    clocks = sampler.stop()
+    _, _, imad_peak = load_peaks()
+    k_ms = tm["main_kernel_ms"]
+    line = {
+        "metric": "secp256k1 ECDSA verifies/sec", "value": value, "unit": "verifies/s", "n_gpus": N, "steps": args.steps,
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (integer, exact)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": n, "launch": "single process, eb200_init(devices[], %d)" % N,
+                   "parallelism": "contiguous blocks over %d GPUs inside eb200_ecdsa_verify_batch, one host thread per GPU" % N},
+        "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": n * N * 160, "d2h_bytes_per_step": n * N,
+                "steps": e2e_steps, "pageable": e2e_pageable, "slowest_gpu_kernel_span_ms": k_ms,
+                "api": "one EC.verify_batch_packed -> eb200_ecdsa_verify_batch call over %d x 2^20 items" % N},
+        "gpu_launches": int(tm["launches"]) * 0 + 5 * N * args.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -560,9 +660,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-workloads", action="store_true", help="headline only (development)")
     ap.add_argument("--only", default="", help="comma-separated subset of the extra workloads (development)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus N devices from this one process through the library's own sharding")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_gpu(args)
 

@@ -7,5 +7,6 @@ N-API shim a maintainer would add is in binding/ and INTEGRATION.md) mirroring
 from .ec import EC as ec  # noqa: F401,N813  (reference export name)
 from .eddsa import EDDSA as eddsa  # noqa: F401,N813
 from . import _native  # noqa: F401
+from . import curve  # noqa: F401   (curve.ShortCurve: run-time short Weierstrass parameters, lib/elliptic/curve/short.js)
 
 version = "0.1.0"

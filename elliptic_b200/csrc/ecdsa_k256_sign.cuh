@@ -111,52 +111,59 @@ EB_HD uint8_t k256_mul_g_item(size_t i, const uint8_t* k, const u32* gtab, uint8
   return ST_TRUE;
 }
 
+// One attempt of the loop body of ec/index.js:153-185 for a given nonce k (little-endian limbs, already
+// _truncateToN(k, true)'d): false = the reference `continue`s (k out of range, r = 0 or s = 0).
+EB_HD bool k256_sign_try(size_t i, const u32* k, const u32* ev, const u32* dv, u32 canonical, const u32* gtab,
+                         uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
+  u32 nn[8], R2[8], ns1[8], one8[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  K256N::n(nn); K256N::r2(R2);
+  sub_n<8>(ns1, nn, one8);
+  bool le1 = (k[0] <= 1) && ((k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0);
+  if (le1 || geq_n<8>(k, ns1)) return false;       // ec/index.js:158-159
+  ge_aff kp = k256_mul_g(k, gtab);
+  u32 r[8];
+  copy_n<8>(r, kp.x.v);
+  bool xr_differ = geq_n<8>(r, nn);
+  if (xr_differ) sub_n<8>(r, r, nn);               // kpX.umod(n)
+  if (is_zero_n<8>(r)) return false;
+  u32 km[8], kinv[8], dm[8], rd[8], t[8], s[8];
+  sc_mont_mul(km, k, R2);
+  sc_mont_inv(kinv, km);                           // k^-1, Montgomery form
+  sc_mont_mul(dm, dv, R2);
+  sc_mont_mul(rd, r, dm);                          // r * d mod n
+  u32 cy = add_n<8>(t, rd, ev);
+  if (cy || geq_n<8>(t, nn)) sub_n<8>(t, t, nn);   // + e mod n
+  sc_mont_mul(s, t, kinv);                         // k^-1 (r d + e) mod n
+  if (is_zero_n<8>(s)) return false;
+  u32 rec = (kp.y.v[0] & 1) | (xr_differ ? 2u : 0u);
+  if (canonical) {
+    u32 nh[8];
+    for (int w = 0; w < 8; w++) nh[w] = (nn[w] >> 1) | ((w < 7 ? nn[w + 1] : 0u) << 31);
+    u32 d2[8];
+    bool gt = sub_n<8>(d2, nh, s) != 0;            // s > n/2
+    if (gt) { sub_n<8>(s, nn, s); rec ^= 1; }
+  }
+  store_be<8>(out_r + 32 * i, r);
+  store_be<8>(out_s + 32 * i, s);
+  out_recid[i] = (uint8_t)rec;
+  return true;
+}
+
 // One signature.  e: _truncateToN(msg) (32 bytes BE, < n); priv: the key pair's private scalar
 // (32 bytes BE, already reduced mod n, ec/key.js:76-82).  Writes r, s (32 B BE) and the recovery param.
 EB_HD uint8_t k256_sign_item(size_t i, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,
                              uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
-  u32 nn[8], R2[8], ev[8], dv[8];
-  K256N::n(nn); K256N::r2(R2);
+  u32 ev[8], dv[8];
   load_be<8>(ev, e + 32 * i);
   load_be<8>(dv, priv + 32 * i);
   hmac_drbg drbg;
   drbg_init(&drbg, priv + 32 * i, e + 32 * i);    // entropy = bkey, nonce = msg (ec/index.js:135-148)
-  u32 ns1[8], one8[8] = {1, 0, 0, 0, 0, 0, 0, 0};
-  sub_n<8>(ns1, nn, one8);
   for (int iter = 0; iter < 128; iter++) {
     uint8_t kb[32];
     drbg_generate32(&drbg, kb);
     u32 k[8];
     load_be<8>(k, kb);                             // _truncateToN(k, true): 32 bytes, no shift
-    bool le1 = (k[0] <= 1) && ((k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0);
-    if (le1 || geq_n<8>(k, ns1)) continue;         // ec/index.js:158-159
-    ge_aff kp = k256_mul_g(k, gtab);
-    u32 r[8];
-    copy_n<8>(r, kp.x.v);
-    bool xr_differ = geq_n<8>(r, nn);
-    if (xr_differ) sub_n<8>(r, r, nn);             // kpX.umod(n)
-    if (is_zero_n<8>(r)) continue;
-    u32 km[8], kinv[8], dm[8], rd[8], t[8], s[8];
-    sc_mont_mul(km, k, R2);
-    sc_mont_inv(kinv, km);                         // k^-1, Montgomery form
-    sc_mont_mul(dm, dv, R2);
-    sc_mont_mul(rd, r, dm);                        // r * d mod n
-    u32 cy = add_n<8>(t, rd, ev);
-    if (cy || geq_n<8>(t, nn)) sub_n<8>(t, t, nn); // + e mod n
-    sc_mont_mul(s, t, kinv);                       // k^-1 (r d + e) mod n
-    if (is_zero_n<8>(s)) continue;
-    u32 rec = (kp.y.v[0] & 1) | (xr_differ ? 2u : 0u);
-    if (canonical) {
-      u32 nh[8];
-      for (int w = 0; w < 8; w++) nh[w] = (nn[w] >> 1) | ((w < 7 ? nn[w + 1] : 0u) << 31);
-      u32 d2[8];
-      bool gt = sub_n<8>(d2, nh, s) != 0;          // s > n/2
-      if (gt) { sub_n<8>(s, nn, s); rec ^= 1; }
-    }
-    store_be<8>(out_r + 32 * i, r);
-    store_be<8>(out_s + 32 * i, s);
-    out_recid[i] = (uint8_t)rec;
-    return ST_TRUE;
+    if (k256_sign_try(i, k, ev, dv, canonical, gtab, out_r, out_s, out_recid)) return ST_TRUE;
   }
   return ST_FALSE;   // unreachable in practice (2^-128 per iteration)
 }

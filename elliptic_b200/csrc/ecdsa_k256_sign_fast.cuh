@@ -137,17 +137,26 @@ EB_HD void drbg_first_k(const u32* priv, const u32* msg, u32* k) {
 }
 
 // ---- nonce kernel body
+// kgiven != NULL: the caller's own nonce for this attempt (options.k, ec/index.js:154-157) instead of the DRBG
 EB_HD void k256_sign_nonce_item(size_t i, size_t N, const uint8_t* e, const uint8_t* priv, const u32* gtab, u32* ws,
-                                uint8_t* status) {
+                                uint8_t* status, const uint8_t* kgiven = nullptr) {
   u32 ew[8], dw[8], kw[8], k[8];
+  if (kgiven) {
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
-    const uint8_t* pe = e + 32 * i + 4 * w;
-    const uint8_t* pd = priv + 32 * i + 4 * w;
-    ew[w] = ((u32)pe[0] << 24) | ((u32)pe[1] << 16) | ((u32)pe[2] << 8) | pe[3];
-    dw[w] = ((u32)pd[0] << 24) | ((u32)pd[1] << 16) | ((u32)pd[2] << 8) | pd[3];
+    for (int w = 0; w < 8; w++) {
+      const uint8_t* pk = kgiven + 32 * i + 4 * w;
+      kw[w] = ((u32)pk[0] << 24) | ((u32)pk[1] << 16) | ((u32)pk[2] << 8) | pk[3];
+    }
+  } else {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const uint8_t* pe = e + 32 * i + 4 * w;
+      const uint8_t* pd = priv + 32 * i + 4 * w;
+      ew[w] = ((u32)pe[0] << 24) | ((u32)pe[1] << 16) | ((u32)pe[2] << 8) | pe[3];
+      dw[w] = ((u32)pd[0] << 24) | ((u32)pd[1] << 16) | ((u32)pd[2] << 8) | pd[3];
+    }
+    drbg_first_k(dw, ew, kw);
   }
-  drbg_first_k(dw, ew, kw);
 #pragma unroll
   for (int w = 0; w < 8; w++) k[w] = kw[7 - w];           // little-endian limbs
   u32 nn[8], ns1[8], one8[8] = {1, 0, 0, 0, 0, 0, 0, 0};

@@ -44,18 +44,24 @@ template <class C, class H>
 struct SignDrbg<C, H, false> {
   static constexpr int N = C::N;
   HmacDrbgB<H> g;
-  EB_HD void init(const uint8_t* priv, const uint8_t* msg) { g.init(priv, C::LEN, msg, C::LEN); }
-  EB_HD void next_k(u32* k) {
-    uint8_t kb[C::LEN];
-    g.generate(kb, C::LEN);                                  // drbg.generate(n.byteLength())
+  EB_HD void init(const uint8_t* priv, const uint8_t* msg, const uint8_t* pers = nullptr, int np = 0) {
+    g.init(priv, C::LEN, msg, C::LEN, pers, np);
+  }
+  // _truncateToN(k, true) (ec/index.js:81-108, BN input) of a LEN-byte big-endian value: the shift is taken from
+  // the VALUE's byte length
+  static EB_HD void truncate_k(u32* k, const uint8_t* kb) {
     load_be_len<N>(k, kb, C::LEN);
-    // _truncateToN(k, true) (ec/index.js:81-108, BN input): the shift is taken from the VALUE's byte length
     int top = 0;
     while (top < C::LEN && kb[top] == 0) top++;
     int delta = 8 * (C::LEN - top) - C::BITS;
     if (delta > 0) {
       for (int w = 0; w < N; w++) k[w] = (k[w] >> delta) | ((w + 1 < N ? k[w + 1] : 0u) << (32 - delta));
     }
+  }
+  EB_HD void next_k(u32* k) {
+    uint8_t kb[C::LEN];
+    g.generate(kb, C::LEN);                                  // drbg.generate(n.byteLength())
+    truncate_k(k, kb);
   }
 };
 
@@ -111,12 +117,17 @@ struct SWSign {
     return acc;
   }
 
+  // kgiven != NULL: the caller's own nonce for this attempt (options.k, ec/index.js:154-157) instead of the DRBG
   static EB_HD void nonce_item(size_t i, size_t cnt, const uint8_t* e, const uint8_t* priv, const u32* gtab, u32* ws,
-                               uint8_t* status) {
-    Drbg g;
-    g.init(priv + C::LEN * i, e + C::LEN * i);
+                               uint8_t* status, const uint8_t* kgiven = nullptr) {
     u32 k[N];
-    g.next_k(k);
+    if (kgiven) {
+      SignDrbg<C, H, false>::truncate_k(k, kgiven + C::LEN * i);
+    } else {
+      Drbg g;
+      g.init(priv + C::LEN * i, e + C::LEN * i);
+      g.next_k(k);
+    }
     bool ok = k_in_range(k);
     jac acc = W::infinity();
     if (ok) acc = mul_g_jac(k, gtab);
@@ -201,6 +212,52 @@ struct SWSign {
     }
   }
 
+  // the same loop with the `pers` option (ec/index.js:143-151): seed = key || msg || pers, byte-stream generator
+  static EB_HD uint8_t slow_item_pers(size_t i, const uint8_t* e, const uint8_t* priv, const uint8_t* pers, int np,
+                                      u32 canonical, const u32* gtab, uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
+    SignDrbg<C, H, false> g;
+    g.init(priv + C::LEN * i, e + C::LEN * i, pers, np);
+    for (int iter = 0; iter < 128; iter++) {
+      u32 k[N];
+      g.next_k(k);
+      if (!k_in_range(k)) continue;
+      aff kp = W::to_aff(mul_g_jac(k, gtab));
+      sc km;
+      copy_n<N>(km.v, k);
+      sc kinv = S::inv(S::to_mont(km));
+      if (finish_one(i, kp.x, kp.y, kinv, e, priv, canonical, out_r, out_s, out_recid)) return 1;
+    }
+    return 0;
+  }
+
+  // EC.genKeyPair (ec/index.js:55-79): HmacDRBG(hash, entropy, nonce = n.toArray(), pers); the first candidate
+  // priv = BN(generate(n.byteLength())) with priv <= n - 2, plus one.  Writes LEN bytes big-endian.
+  static EB_HD uint8_t keygen_item(size_t i, const uint8_t* entropy, int ne, const uint8_t* pers, int np, uint8_t* out_priv) {
+    HmacDrbgB<H> g;
+    u32 nmod[N], ns2[N], two[N];
+    W::n_limbs(nmod);
+    for (int w = 0; w < N; w++) two[w] = w == 0 ? 2u : 0u;
+    sub_n<N>(ns2, nmod, two);
+    uint8_t nb[C::LEN];
+    store_be_len<N>(nb, nmod, C::LEN);
+    g.init(entropy + (size_t)ne * i, ne, nb, C::LEN, pers, np);
+    for (int iter = 0; iter < 65536; iter++) {
+      uint8_t kb[C::LEN];
+      g.generate(kb, C::LEN);
+      bool fits = true;                                     // the raw value may be wider than the limb array holds (p521: 528 bits)
+      for (int b = 0; b < C::LEN - 4 * N; b++) fits = fits && kb[b] == 0;
+      u32 k[N];
+      load_be_len<N>(k, kb, C::LEN);
+      if (!fits || (geq_n<N>(k, ns2) && !eq_n<N>(k, ns2))) continue;     // priv.cmp(ns2) > 0
+      u32 one[N];
+      for (int w = 0; w < N; w++) one[w] = w == 0;
+      add_n<N>(k, k, one);
+      store_be_len<N>(out_priv + C::LEN * i, k, C::LEN);
+      return 1;
+    }
+    return 0;
+  }
+
   // the literal loop of ec/index.js:153-185 for one flagged item
   static EB_HD uint8_t slow_item(size_t i, const uint8_t* e, const uint8_t* priv, u32 canonical, const u32* gtab,
                                  uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
@@ -219,5 +276,43 @@ struct SWSign {
     return 0;
   }
 };
+
+// secp256k1: EC.sign with the `pers` option and EC.genKeyPair on the byte-stream generator (SHA-256)
+EB_HD uint8_t k256_sign_item_pers(size_t i, const uint8_t* e, const uint8_t* priv, const uint8_t* pers, int np, u32 canonical,
+                                  const u32* gtab, uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid) {
+  u32 ev[8], dv[8];
+  load_be<8>(ev, e + 32 * i);
+  load_be<8>(dv, priv + 32 * i);
+  HmacDrbgB<Sha256W> g;
+  g.init(priv + 32 * i, 32, e + 32 * i, 32, pers, np);
+  for (int iter = 0; iter < 128; iter++) {
+    uint8_t kb[32];
+    g.generate(kb, 32);
+    u32 k[8];
+    load_be<8>(k, kb);
+    if (k256_sign_try(i, k, ev, dv, canonical, gtab, out_r, out_s, out_recid)) return ST_TRUE;
+  }
+  return ST_FALSE;
+}
+EB_HD uint8_t k256_keygen_item(size_t i, const uint8_t* entropy, int ne, const uint8_t* pers, int np, uint8_t* out_priv) {
+  u32 nn[8], ns2[8], two[8] = {2, 0, 0, 0, 0, 0, 0, 0}, one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  K256N::n(nn);
+  sub_n<8>(ns2, nn, two);
+  uint8_t nb[32];
+  store_be<8>(nb, nn);
+  HmacDrbgB<Sha256W> g;
+  g.init(entropy + (size_t)ne * i, ne, nb, 32, pers, np);
+  for (int iter = 0; iter < 65536; iter++) {
+    uint8_t kb[32];
+    g.generate(kb, 32);
+    u32 k[8];
+    load_be<8>(k, kb);
+    if (geq_n<8>(k, ns2) && !eq_n<8>(k, ns2)) continue;       // priv.cmp(ns2) > 0
+    add_n<8>(k, k, one);
+    store_be<8>(out_priv + 32 * i, k);
+    return ST_TRUE;
+  }
+  return ST_FALSE;
+}
 
 }  // namespace eb

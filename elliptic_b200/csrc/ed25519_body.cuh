@@ -271,23 +271,117 @@ EB_HD void ed25519_hash_item(size_t i, const uint8_t* Rb, const uint8_t* Ab, con
 }
 
 // ---------------------------------------------------------------------------
+// EDDSA.prototype.sign (eddsa/index.js:34-44) with KeyPair.fromSecret (eddsa/key.js:52-75):
+//   hash = SHA512(secret);  a = clamp(hash[0..31]);  prefix = hash[32..63];  A = a*G
+//   r = SHA512(prefix || M) mod n;  R = r*G;  S = (r + SHA512(Renc || Aenc || M) * a) mod n;  sig = Renc || S
+// Both scalar multiplications are fixed-base (the verify kernel's 13-bit window table, 20 additions each).
+
+// s * G for a 256-bit little-endian scalar s < 2^255 (signed 13-bit windows over the niels table)
+EB_HD ed_ext ed_mul_base(const u32* s, const u32* gtab) {
+  u32 S[8];
+  {
+    const u32 c19[8] = {0x02001000u, 0x00080040u, 0x04002001u, 0x00100080u, 0x08004002u, 0x00200100u, 0x10008004u, 0x00400200u};
+    add_n<8>(S, s, c19);
+  }
+  ed_ext acc = ed_identity();
+  for (int j = 0; j < ED_GWINDOWS; j++) {
+    int pos = ED_GW * j, wi = pos >> 5;
+    u32 lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { lo = (k == wi) ? S[k] : lo; hi = (k == wi + 1) ? S[k] : hi; }
+    u64 both = ((u64)hi << 32) | lo;
+    int chunk = (int)((u32)(both >> (pos & 31)) & ((1u << ED_GW) - 1));
+    int dg = (j == ED_GWINDOWS - 1) ? chunk : chunk - (1 << (ED_GW - 1));
+    bool neg = dg < 0;
+    u32 idx = (u32)(neg ? -dg : dg);
+    const u32* ent = gtab + ((size_t)j * ED_GENTRIES + idx) * 24;
+    ed_niels q;
+    q.ypx = f25_load(ent); q.ymx = f25_load(ent + 8); q.t2d = f25_load(ent + 16);
+    acc = ed_add_niels(acc, ed_niels_neg_if(q, neg));
+  }
+  return acc;
+}
+// EDDSA.encodePoint (eddsa/index.js:94-98): y little-endian, x parity in the top bit
+EB_HD void ed_encode(const ed_ext& p, uint8_t* out32) {
+  f25 zi = f25_inv(p.z);
+  f25 x = f25_normalize(f25_mul(p.x, zi)), y = f25_normalize(f25_mul(p.y, zi));
+  for (int k = 0; k < 8; k++) {
+    out32[4 * k] = (uint8_t)y.v[k]; out32[4 * k + 1] = (uint8_t)(y.v[k] >> 8);
+    out32[4 * k + 2] = (uint8_t)(y.v[k] >> 16); out32[4 * k + 3] = (uint8_t)(y.v[k] >> 24);
+  }
+  out32[31] |= (x.v[0] & 1) ? 0x80 : 0;
+}
+// 64-byte digest as a little-endian integer mod n, Montgomery form of the scalar field
+EB_HD Fp<ED25519_FN>::fe ed_digest_mod_n(const uint8_t* dg) {
+  typedef Fp<ED25519_FN> S;
+  S::fe lo, hi;
+  load_le<8>(lo.v, dg);
+  load_le<8>(hi.v, dg + 32);
+  // to_mont(lo) = lo R ; to_mont(to_mont(hi)) = hi R^2 = (hi 2^256) R
+  return S::add(S::to_mont(lo), S::to_mont(S::to_mont(hi)));
+}
+// secrets: N x 32 bytes; msgs + msg_off: concatenated messages; sig: N x 64 out; pub: N x 32 out or NULL
+EB_HD uint8_t ed25519_sign_item(size_t i, const uint8_t* secrets, const uint8_t* msgs, const u64* msg_off,
+                                const u32* gtab, uint8_t* sig, uint8_t* pub) {
+  typedef Fp<ED25519_FN> S;
+  uint8_t hash[64], dg[64], aenc[32];
+  sha512_ctx c;
+  sha512_init(&c);
+  sha512_update(&c, secrets + 32 * i, 32);
+  sha512_final(&c, hash);
+  hash[0] &= 248; hash[31] &= 127; hash[31] |= 64;                  // eddsa/key.js:58-62
+  u32 a[8];
+  load_le<8>(a, hash);
+  ed_encode(ed_mul_base(a, gtab), aenc);                            // pubBytes
+  if (pub) for (int k = 0; k < 32; k++) pub[32 * i + k] = aenc[k];
+  const uint8_t* m = msgs + msg_off[i];
+  const size_t ml = (size_t)(msg_off[i + 1] - msg_off[i]);
+  sha512_init(&c);
+  sha512_update(&c, hash + 32, 32);                                 // messagePrefix
+  sha512_update(&c, m, ml);
+  sha512_final(&c, dg);
+  S::fe r = ed_digest_mod_n(dg);
+  S::fe rp = S::from_mont(r);                                       // r < n, plain
+  uint8_t* renc = sig + 64 * i;
+  ed_encode(ed_mul_base(rp.v, gtab), renc);
+  sha512_init(&c);
+  sha512_update(&c, renc, 32);
+  sha512_update(&c, aenc, 32);
+  sha512_update(&c, m, ml);
+  sha512_final(&c, dg);
+  S::fe h = ed_digest_mod_n(dg);
+  S::fe am; for (int k = 0; k < 8; k++) am.v[k] = a[k];
+  S::fe sv = S::from_mont(S::add(r, S::mul(h, S::to_mont(am))));    // (r + h a) mod n
+  for (int k = 0; k < 8; k++) {
+    sig[64 * i + 32 + 4 * k] = (uint8_t)sv.v[k]; sig[64 * i + 32 + 4 * k + 1] = (uint8_t)(sv.v[k] >> 8);
+    sig[64 * i + 32 + 4 * k + 2] = (uint8_t)(sv.v[k] >> 16); sig[64 * i + 32 + 4 * k + 3] = (uint8_t)(sv.v[k] >> 24);
+  }
+  // the clamped key and the nonce must not stay in local memory beyond this call
+  for (int k = 0; k < 64; k++) hash[k] = 0;
+  return 1;
+}
+
+// ---------------------------------------------------------------------------
 // curve25519 ECDH: KeyPair.derive (ec/key.js:102-107).  priv, pubx: 32 bytes big-endian
 // (priv as held by the key pair, i.e. already reduced mod n at import, ec/key.js:76-82).
 // out: 32-byte big-endian x.  Status 1 = value returned, 5 = the reference throws
 // 'Assertion failed' (Red.sqrt on a non-residue inside MontCurve.validate, mont.js:21-28).
-EB_HD uint8_t x25519_derive_item(size_t i, const uint8_t* priv, const uint8_t* pubx, uint8_t* out) {
+template <bool VALIDATE>
+EB_HD uint8_t x25519_ladder_item(size_t i, const uint8_t* priv, const uint8_t* pubx, uint8_t* out) {
   u32 k[8];
   load_be<8>(k, priv + 32 * i);
   f25 x;
   load_be<8>(x.v, pubx + 32 * i);                     // toRed reduces mod p; weak form is fine here
-  // validate: x^3 + A x^2 + x must be a square (or 0)
-  f25 x2 = f25_sqr(x);
-  f25 rhs = f25_add(f25_add(f25_mul(x2, x), f25_mul_small(x2, 486662u)), x);
-  f25 leg = f25_normalize(f25_legendre(rhs));
-  bool is_qr = is_zero_n<8>(leg.v) || (leg.v[0] == 1 && (leg.v[1] | leg.v[2] | leg.v[3] | leg.v[4] | leg.v[5] | leg.v[6] | leg.v[7]) == 0);
-  if (!is_qr) {
-    for (int b = 0; b < 32; b++) out[32 * i + b] = 0;
-    return 5;
+  if (VALIDATE) {
+    // validate: x^3 + A x^2 + x must be a square (or 0)
+    f25 x2 = f25_sqr(x);
+    f25 rhs = f25_add(f25_add(f25_mul(x2, x), f25_mul_small(x2, 486662u)), x);
+    f25 leg = f25_normalize(f25_legendre(rhs));
+    bool is_qr = is_zero_n<8>(leg.v) || (leg.v[0] == 1 && (leg.v[1] | leg.v[2] | leg.v[3] | leg.v[4] | leg.v[5] | leg.v[6] | leg.v[7]) == 0);
+    if (!is_qr) {
+      for (int b = 0; b < 32; b++) out[32 * i + b] = 0;
+      return 5;
+    }
   }
   // Montgomery ladder, MSB first (mont.js:130-153): (a, b) = ((m+1)P, mP), diff = P = (x : 1)
   f25 ax = x, az = f25_one(), bx = f25_one(), bz = f25_zero();
@@ -316,6 +410,13 @@ EB_HD uint8_t x25519_derive_item(size_t i, const uint8_t* priv, const uint8_t* p
   f25 r = f25_normalize(f25_mul(bx, f25_inv(bz)));    // getX: x * z^-1, with inv(0) = 0 (mont.js:167-178)
   store_be<8>(out + 32 * i, r.v);
   return 1;
+}
+EB_HD uint8_t x25519_derive_item(size_t i, const uint8_t* priv, const uint8_t* pubx, uint8_t* out) {
+  return x25519_ladder_item<true>(i, priv, pubx, out);
+}
+// MontCurve Point.mul(k).getX() (mont.js:130-153, 173-178): the ladder over all 256 bits of k, no validation
+EB_HD uint8_t x25519_mul_item(size_t i, const uint8_t* k, const uint8_t* px, uint8_t* out) {
+  return x25519_ladder_item<false>(i, k, px, out);
 }
 
 }  // namespace eb

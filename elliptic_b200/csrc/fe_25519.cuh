@@ -11,7 +11,7 @@
 #ifndef EB_SQR8_INCLUDED
 #define EB_SQR8_INCLUDED
 namespace eb {
-#include "sqr8_gen.inc"
+#include "sqr_gen.inc"
 }
 #endif
 #endif

@@ -120,11 +120,11 @@ EB_HD void fe_reduce512(u32* r, const u32* t) {
 }
 
 // Squaring: 36 MACs (28 off-diagonal products once, doubled, + 8 squares) as PTX
-// carry chains generated by tools/gen_sqr8.py; the host-emulation build uses the
+// carry chains generated by tools/gen_sqr.py; the host-emulation build uses the
 // general product.
 #if defined(__CUDACC__) && !defined(EB_SQR8_INCLUDED)
 #define EB_SQR8_INCLUDED
-#include "sqr8_gen.inc"
+#include "sqr_gen.inc"
 #endif
 EB_HD void fe_sqr_wide(u32* r, const u32* a) {
 #if defined(__CUDA_ARCH__) && !defined(EB_SQR_AS_MUL)

@@ -1,0 +1,240 @@
+// fp_special.cuh -- prime-field arithmetic for the NIST primes with their own fast reductions:
+//   p256 = 2^256 - 2^224 + 2^192 + 2^96 - 1,  p384 = 2^384 - 2^128 - 2^96 + 2^32 - 1,  p521 = 2^521 - 1.
+//
+// The reference runs these curves on bn.js `Mont` (lib/elliptic/curves.js:73-134 give `prime: null` ->
+// BN.mont(p), curve/base.js:14; Mont.mul / imul dist/elliptic.js:7312-7381): every product is followed by an
+// N x N multiplication by the modulus.  Only canonical residues are observable (fromRed), so the engine is
+// free to hold PLAIN residues and reduce the double-width product with the primes' word structure instead
+// (FIPS 186-4 D.2): word additions / subtractions of the high half for p256 / p384, one 521-bit fold for
+// p521.  Against the generic CIOS of fp_mont.cuh that drops N^2 + N of the 2 N^2 + N multiplies of a product
+// and lets squarings use the N (N + 1) / 2-multiply generated squarer (tools/gen_sqr.py).
+//
+// Same interface as Fp<P> (fp_mont.cuh), so SW<C> (ecdsa_sw_body.cuh) is unchanged: `to_mont` reduces a raw
+// value mod p (the reference's toRed, dist:7292-7296), `from_mont` is the identity, `one()` is 1.
+#pragma once
+#include "fp_mont.cuh"
+
+namespace eb {
+
+#if defined(__CUDACC__) && !defined(EB_SQR8_INCLUDED)
+#define EB_SQR8_INCLUDED
+#include "sqr_gen.inc"
+#endif
+
+// acc (N words) += / -= v, returns the carry / borrow
+template <int N> EB_HD int sp_addv(u32* acc, const u32* v) { return (int)add_n<N>(acc, acc, v); }
+template <int N> EB_HD int sp_subv(u32* acc, const u32* v) { return (int)sub_n<N>(acc, acc, v); }
+
+// acc += u * K (u small); returns the carry word
+template <int N> EB_HD u32 sp_addmul_small(u32* acc, const u32* K, u32 u) {
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    c += (u64)K[j] * u + acc[j];
+    acc[j] = (u32)c;
+    c >>= 32;
+  }
+  return (u32)c;
+}
+// (carry, acc) < 2p  ->  canonical residue
+template <int N> EB_HD void sp_final(u32* r, const u32* acc, u32 carry, const u32* p) {
+  u32 d[N];
+  u32 bw = sub_n<N>(d, acc, p);
+  bool ge = carry != 0 || bw == 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) r[i] = ge ? d[i] : acc[i];
+}
+
+// r = a + b + c word-wise with the carries counted (a, b, c: N words); returns the carry count (0..2)
+template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32* c) {
+  int t = (int)add_n<N>(r, a, b);
+  return t + (int)add_n<N>(r, r, c);
+}
+
+// ---- p256: r = s1 + 2 s2 + 2 s3 + s4 + s5 - s6 - s7 - s8 - s9  (FIPS 186-4 D.2.3; word vectors (w7..w0)) ----
+// The nine vectors are summed as four independent carry chains (two positive, two negative) that are only
+// joined at the end: the chains of a naive left-to-right sum are ~90 dependent add-with-carry instructions, and
+// with two warps per scheduler that latency, not the instruction count, sets the pace.
+struct RedP256 {
+  static constexpr int N = 8, WN = 8;
+  static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
+    // value = acc + top * 2^256, top in [-4, 5].  2^256 = K (mod p), K = 2^224 - 2^192 - 2^96 + 1:
+    // acc + (top + 4) K + (-4 K mod p), all terms non-negative; C4 = -4 K mod p rides along with s1
+    const u32 K[8] = {0x00000001u, 0, 0, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfffffffeu, 0};
+    const u32 C4[8] = {0xfffffffbu, 0xffffffffu, 0xffffffffu, 0x00000004u, 0x00000000u, 0x00000000u, 0x00000005u, 0xfffffffbu};
+    const u32 s2[8] = {0, 0, 0, c[11], c[12], c[13], c[14], c[15]};
+    const u32 s3[8] = {0, 0, 0, c[12], c[13], c[14], c[15], 0};
+    const u32 s4[8] = {c[8], c[9], c[10], 0, 0, 0, c[14], c[15]};
+    const u32 s5[8] = {c[9], c[10], c[11], c[13], c[14], c[15], c[13], c[8]};
+    const u32 s6[8] = {c[11], c[12], c[13], 0, 0, 0, c[8], c[10]};
+    const u32 s7[8] = {c[12], c[13], c[14], c[15], 0, 0, c[9], c[11]};
+    const u32 s8[8] = {c[13], c[14], c[15], c[8], c[9], c[10], 0, c[12]};
+    const u32 s9[8] = {c[14], c[15], 0, c[9], c[10], c[11], 0, c[13]};
+    u32 p1[8], p2[8], p3[8], n1[8], n2[8];
+    int top = sp_add3<8>(p1, c, C4, s2);               // s1 + C4 + s2
+    top += sp_add3<8>(p2, s2, s3, s3);                 // s2 + 2 s3
+    top += (int)add_n<8>(p3, s4, s5);
+    top -= (int)add_n<8>(n1, s6, s7);
+    top -= (int)add_n<8>(n2, s8, s9);
+    u32 acc[8];
+    top += sp_add3<8>(acc, p1, p2, p3);
+    top -= (int)sub_n<8>(acc, acc, n1);
+    top -= (int)sub_n<8>(acc, acc, n2);
+    u32 cy = sp_addmul_small<8>(acc, K, (u32)(top + 4));
+    sp_final<8>(r, acc, cy, p);
+  }
+};
+
+// ---- p384: r = s1 + 2 s2 + s3 + s4 + s5 + s6 + s7 - s8 - s9 - s10  (FIPS 186-4 D.2.4) ----------------------
+struct RedP384 {
+  static constexpr int N = 12, WN = 12;
+  static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
+    // value = acc + top * 2^384, top in [-3, 7].  2^384 = K (mod p), K = 2^128 + 2^96 - 2^32 + 1; C3 = -3 K mod p
+    const u32 K[12] = {0x00000001u, 0xffffffffu, 0xffffffffu, 0, 0x00000001u, 0, 0, 0, 0, 0, 0, 0};
+    const u32 C3[12] = {0xfffffffcu, 0x00000003u, 0x00000000u, 0xfffffffcu, 0xfffffffbu, 0xffffffffu,
+                        0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    const u32 s2[12] = {0, 0, 0, 0, c[21], c[22], c[23], 0, 0, 0, 0, 0};
+    const u32 s4[12] = {c[21], c[22], c[23], c[12], c[13], c[14], c[15], c[16], c[17], c[18], c[19], c[20]};
+    const u32 s5[12] = {0, c[23], 0, c[20], c[12], c[13], c[14], c[15], c[16], c[17], c[18], c[19]};
+    const u32 s6[12] = {0, 0, 0, 0, c[20], c[21], c[22], c[23], 0, 0, 0, 0};
+    const u32 s7[12] = {c[20], 0, 0, c[21], c[22], c[23], 0, 0, 0, 0, 0, 0};
+    const u32 s8[12] = {c[23], c[12], c[13], c[14], c[15], c[16], c[17], c[18], c[19], c[20], c[21], c[22]};
+    const u32 s9[12] = {0, c[20], c[21], c[22], c[23], 0, 0, 0, 0, 0, 0, 0};
+    const u32 s10[12] = {0, 0, 0, c[23], c[23], 0, 0, 0, 0, 0, 0, 0};
+    u32 p1[12], p2[12], p3[12], n1[12];
+    int top = sp_add3<12>(p1, c, C3, c + 12);          // s1 + C3 + s3
+    top += sp_add3<12>(p2, s2, s2, s4);
+    top += sp_add3<12>(p3, s5, s6, s7);
+    top -= sp_add3<12>(n1, s8, s9, s10);
+    u32 acc[12];
+    top += sp_add3<12>(acc, p1, p2, p3);
+    top -= (int)sub_n<12>(acc, acc, n1);
+    u32 cy = sp_addmul_small<12>(acc, K, (u32)(top + 3));
+    sp_final<12>(r, acc, cy, p);
+  }
+};
+
+// ---- p521 = 2^521 - 1 in an 18-word container (521 bits = 16 words + 9 bits; word 17 is always 0) -------------
+struct RedP521 {
+  static constexpr int N = 18, WN = 17;
+  static EB_HD void reduce(u32* r, const u32* c, const u32* /*p*/) {
+    // c < 2^1042 (36 words, the top ones zero): (c mod 2^521) + (c >> 521), twice, then p -> 0
+    u32 lo[17], hi[17];
+#pragma unroll
+    for (int i = 0; i < 16; i++) lo[i] = c[i];
+    lo[16] = c[16] & 0x1ffu;
+#pragma unroll
+    for (int i = 0; i < 17; i++) hi[i] = (c[16 + i] >> 9) | (c[17 + i] << 23);
+    add_n<17>(lo, lo, hi);                       // < 2^522: no carry out of word 16
+    u32 k = lo[16] >> 9;
+    lo[16] &= 0x1ffu;
+    u32 one[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) one[i] = i == 0 ? k : 0u;
+    add_n<17>(lo, lo, one);                      // <= 2^521 - 1 (see the derivation in DESIGN.md: the sum was <= 2^522 - 2)
+    u32 all = lo[16] ^ 0x1ffu;
+#pragma unroll
+    for (int i = 0; i < 16; i++) all |= ~lo[i];
+    bool is_p = all == 0;
+#pragma unroll
+    for (int i = 0; i < 17; i++) r[i] = is_p ? 0u : lo[i];
+    r[17] = 0;
+  }
+};
+
+template <class P, class RED>
+struct FpS {
+  static constexpr int N = P::N;
+  typedef P Params;
+  typedef fe_n<N> fe;
+  typedef Fp<P> G;                       // generic canonical add / sub / compare
+
+  static EB_HD fe zero() { fe r; for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
+  static EB_HD fe one() { fe r = zero(); r.v[0] = 1; return r; }
+
+  static EB_HD fe mul_inl(const fe& a, const fe& b) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+    mul_wide<N>(t, a.v, b.v);
+    t[2 * N] = 0; t[2 * N + 1] = 0;
+    fe r;
+    RED::reduce(r.v, t, p);
+    return r;
+  }
+  static EB_HD fe sqr_inl(const fe& a) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+#if defined(__CUDA_ARCH__) && !defined(EB_SQR_AS_MUL)
+    if (RED::WN == 8) sqr_wide8_ptx(t, a.v);
+    else if (RED::WN == 12) sqr_wide12_ptx(t, a.v);
+    else { sqr_wide17_ptx(t, a.v); t[34] = 0; t[35] = 0; }
+#else
+    mul_wide<N>(t, a.v, a.v);
+#endif
+    t[2 * N] = 0; t[2 * N + 1] = 0;
+    fe r;
+    RED::reduce(r.v, t, p);
+    return r;
+  }
+#if defined(__CUDACC__)
+  static __device__ __noinline__ fe mul_ol(fe a, fe b) { return mul_inl(a, b); }
+  static __device__ __noinline__ fe sqr_ol(fe a) { return sqr_inl(a); }
+#endif
+  static EB_HD fe mul(const fe& a, const fe& b) {
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
+    return mul_ol(a, b);
+#else
+    return mul_inl(a, b);
+#endif
+  }
+  static EB_HD fe sqr(const fe& a) {
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
+    return sqr_ol(a);
+#else
+    return sqr_inl(a);
+#endif
+  }
+
+  static EB_HD fe add(const fe& a, const fe& b) { return G::add(a, b); }
+  static EB_HD fe sub(const fe& a, const fe& b) { return G::sub(a, b); }
+  static EB_HD fe neg(const fe& a) { return G::sub(zero(), a); }
+  static EB_HD fe dbl(const fe& a) { return G::add(a, a); }
+  static EB_HD bool is_zero(const fe& a) { return is_zero_n<N>(a.v); }
+  static EB_HD bool eq(const fe& a, const fe& b) { return eq_n<N>(a.v, b.v); }
+  static EB_HD fe cmov(const fe& a, const fe& b, bool c) { return G::cmov(a, b, c); }
+
+  // raw integer (< 2^(32N)) -> residue (`toRed`): reduce as a double-width value whose high half is zero
+  static EB_HD fe to_mont(const fe& a) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+#pragma unroll
+    for (int i = 0; i < 2 * N + 2; i++) t[i] = i < N ? a.v[i] : 0u;
+    fe r;
+    RED::reduce(r.v, t, p);
+    return r;
+  }
+  static EB_HD fe from_mont(const fe& a) { return a; }
+  static EB_HD bool geq_mod(const u32* a) { u32 p[N]; P::mod(p); return geq_n<N>(a, p); }
+
+  static EB_HD fe pow(const fe& a, const u32* e) {
+    fe r = one();
+    bool started = false;
+    for (int i = 32 * N - 1; i >= 0; i--) {
+      if (started) r = sqr(r);
+      if ((e[i >> 5] >> (i & 31)) & 1) {
+        r = started ? mul(r, a) : a;
+        started = true;
+      }
+    }
+    return r;
+  }
+  static EB_HD fe inv(const fe& a) {
+    u32 e[N], two[N];
+    P::mod(e);
+    for (int i = 0; i < N; i++) two[i] = i == 0 ? 2u : 0u;
+    sub_n<N>(e, e, two);
+    return pow(a, e);
+  }
+};
+
+}  // namespace eb

@@ -258,8 +258,9 @@ struct HmacDrbgB {
     s.start(iv, 0); s.absorb(pad, BB);
     for (int i = 0; i < 8; i++) kout[i] = s.st[i];
   }
-  // HMAC(K, V || [sep] || a || b)
-  EB_HD void mac(bool with_sep, uint8_t sep, const uint8_t* a, int na, const uint8_t* b, int nb, uint8_t* out) const {
+  // HMAC(K, V || [sep] || a || b || c)
+  EB_HD void mac(bool with_sep, uint8_t sep, const uint8_t* a, int na, const uint8_t* b, int nb, uint8_t* out,
+                 const uint8_t* c = nullptr, int nc = 0) const {
     HashStreamW<H> s;
     uint8_t inner[DB];
     s.start(kin, BB);
@@ -267,19 +268,21 @@ struct HmacDrbgB {
     if (with_sep) s.absorb(&sep, 1);
     if (na) s.absorb(a, na);
     if (nb) s.absorb(b, nb);
+    if (nc) s.absorb(c, nc);
     s.finish(inner, DB);
     s.start(kout, BB);
     s.absorb(inner, DB);
     s.finish(out, DB);
   }
-  EB_HD void init(const uint8_t* entropy, int ne, const uint8_t* nonce, int nn) {
+  // seed = entropy || nonce || pers  (HmacDRBG._init, dist:8719-8733)
+  EB_HD void init(const uint8_t* entropy, int ne, const uint8_t* nonce, int nn, const uint8_t* pers = nullptr, int np = 0) {
     uint8_t K[DB];
     for (int i = 0; i < DB; i++) { K[i] = 0x00; V[i] = 0x01; }
     set_key(K);
-    mac(true, 0x00, entropy, ne, nonce, nn, K);
+    mac(true, 0x00, entropy, ne, nonce, nn, K, pers, np);
     set_key(K);
     mac(false, 0, nullptr, 0, nullptr, 0, V);
-    mac(true, 0x01, entropy, ne, nonce, nn, K);
+    mac(true, 0x01, entropy, ne, nonce, nn, K, pers, np);
     set_key(K);
     mac(false, 0, nullptr, 0, nullptr, 0, V);
     first = true;

@@ -30,12 +30,17 @@ _CURVES = {
     "p521": dict(id=nat.CURVE_P521, len=66,
                  n=0x1fffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffffa51868783bf2f966b7fcc0148f709a5d03bb5c9b8899c47aebb6fb71e91386409,
                  p=2**521 - 1),
+    "ed25519": dict(id=nat.CURVE_ED25519, len=32,
+                    n=0x1000000000000000000000000000000014def9dea2f79cd65812631a5cf5d3ed, p=2**255 - 19),
     "p192": dict(id=nat.CURVE_P192, len=24, n=0xffffffffffffffffffffffff99def836146bc9b1b4d22831, p=0xfffffffffffffffffffffffffffffffeffffffffffffffff),
     "p224": dict(id=nat.CURVE_P224, len=28, n=0xffffffffffffffffffffffffffff16a2e0b8f03e13dd29455c5c2a3d, p=0xffffffffffffffffffffffffffffffff000000000000000000000001),
 }
 
 
 _SHORT = ("secp256k1", "p256", "p384", "p521", "p192", "p224")
+# presets whose points are (x, y) pairs with batch sign / keygen / mul / mulAdd / ECDH entry points: the six short
+# curves and the twisted Edwards preset (new elliptic.ec('ed25519'), test/ecdsa-test.js:130, test/ecdh-test.js:26)
+_XY = _SHORT + ("ed25519",)
 
 
 class EllipticError(Exception):
@@ -88,12 +93,32 @@ def _to_array(msg, enc=None):
     raise TypeError("unsupported input form")
 
 
+def _parse_hex(s):
+    """bn.js 4.11.9 `new BN(str, 16)` (dist/elliptic.js:4135-4157 parseHex, :4003-4017): whitespace is dropped, a
+    leading '-' negates, and a character outside [0-9a-fA-F] contributes (charCode - 48) & 0xf instead of throwing."""
+    s = "".join(s.split())
+    neg = s.startswith("-")
+    if neg:
+        s = s[1:]
+    v = 0
+    for ch in s:
+        c = ord(ch) - 48
+        if 49 <= c <= 54:
+            d = c - 49 + 10
+        elif 17 <= c <= 22:
+            d = c - 17 + 10
+        else:
+            d = c & 0xF
+        v = (v << 4) | d
+    return -v if neg else v
+
+
 def _bn(v):
     """`new BN(v, 16)` for int / hex string / byte array."""
     if isinstance(v, int):
         return v
     if isinstance(v, str):
-        return int(v, 16) if v else 0
+        return _parse_hex(v)
     return int.from_bytes(bytes(v), "big")
 
 
@@ -167,14 +192,13 @@ class EC:
 
     # ---- reference-compatible scalar preparation (host side, cheap) -------------
     def _truncate_to_n(self, msg, msg_bit_length=None):
-        """EC._truncateToN (ec/index.js:81-108) up to, but not including, the
-        conditional `- n` (the engine reduces mod n itself)."""
+        """EC._truncateToN (ec/index.js:81-108), including its single conditional `- n`."""
         if isinstance(msg, int):
             v = msg
             byte_length = (v.bit_length() + 7) // 8
         elif isinstance(msg, str):
             byte_length = (len(msg) + 1) >> 1
-            v = int(msg, 16) if msg else 0
+            v = _parse_hex(msg)
         else:
             b = _to_array(msg)
             byte_length = len(b)
@@ -252,6 +276,9 @@ class EC:
         off[1:] = np.cumsum([len(d) for d in ders])
         blob = np.frombuffer(b"".join(bytes(d) for d in ders) + b"\x00", np.uint8)
         e = np.ascontiguousarray(e, np.uint8); pub = np.ascontiguousarray(pub, np.uint8)
+        pb = {nat.PUB_XY: 2 * self._len, nat.PUB_SEC1_65: 1 + 2 * self._len, nat.PUB_SEC1_33: 1 + self._len}[pub_fmt]
+        if e.shape != (n, self._len) or pub.shape != (n, pb):
+            raise EllipticError("verify_batch_der_packed: e must be (n, %d) and pub (n, %d)" % (self._len, pb))
         status = np.zeros(n, np.uint8)
         nat.check(lib.eb200_ecdsa_verify_batch_der(self._c["id"], n, e.ctypes.data, blob.ctypes.data, off.ctypes.data,
                                                    pub.ctypes.data, pub_fmt, status.ctypes.data))
@@ -292,32 +319,90 @@ class EC:
         return st
 
     # ---- signing ---------------------------------------------------------------------------------------------
-    def sign_batch(self, msgs, privs, canonical=False, msg_bit_length=None):
-        """Batch of EC.prototype.sign (ec/index.js:110-186) with the default hash and RFC 6979 nonces
-        (no `pers`, no custom `k`).  Returns (r list, s list, recoveryParam array)."""
-        if self.name not in _SHORT:
-            raise EllipticError("sign_batch: short curves only")
+    def sign_batch(self, msgs, privs, canonical=False, msg_bit_length=None, pers=None, pers_enc=None, k=None):
+        """Batch of EC.prototype.sign (ec/index.js:110-186) with the curve's default hash.
+        pers / pers_enc: the `pers` / `persEnc` options (one personalisation string for the batch; persEnc defaults
+        to 'utf8' as in ec/index.js:150).  k: the `k` option as a callable k(item, iter) -> nonce (int / hex / bytes);
+        without it the nonces are RFC 6979 (HMAC-DRBG on the GPU).  Returns (r list, s list, recoveryParam array)."""
+        if self.name not in _XY:
+            raise EllipticError("sign_batch: not available on " + self.name)
         lib = nat.init(self._device)
         n, ln = len(msgs), self._len
         e = np.zeros((n, ln), np.uint8); d = np.zeros((n, ln), np.uint8)
         for i in range(n):
-            ev = self._truncate_to_n(msgs[i], msg_bit_length)
-            if ev >= self.n:
-                ev -= self.n                                                   # ec/index.js:105-106
+            ev = self._truncate_to_n(msgs[i], msg_bit_length)                  # includes the single `- n` (ec/index.js:105-106)
             if ev >> (8 * ln):
-                raise EllipticError("Can not sign message")                    # ec/index.js:136-137
+                raise EllipticError("byte array longer than desired length")   # msg.toArray('be', bytes), dist bn.js toArrayLike
             e[i] = np.frombuffer(ev.to_bytes(ln, "big"), np.uint8)
             d[i] = np.frombuffer((_bn(privs[i]) % self.n).to_bytes(ln, "big"), np.uint8)   # _importPrivate
         r = np.zeros((n, ln), np.uint8); s = np.zeros((n, ln), np.uint8)
         rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
-        nat.check(lib.eb200_ecdsa_sign_batch(self._c["id"], n, e.ctypes.data, d.ctypes.data, 1 if canonical else 0,
-                                             r.ctypes.data, s.ctypes.data, rec.ctypes.data, st.ctypes.data))
-        assert bool((st == nat.ST_TRUE).all())
+        flags = 1 if canonical else 0
+        if k is not None:
+            todo = np.arange(n)
+            for it in range(1 << 16):
+                kb = np.zeros((len(todo), ln), np.uint8)
+                for j, i in enumerate(todo):
+                    kv = _bn(k(int(i), it))
+                    # _truncateToN(k, true) on a BN wider than the field: shift by its own byte length (ec/index.js:96-103)
+                    delta = ((kv.bit_length() + 7) // 8) * 8 - self.n.bit_length()
+                    if kv.bit_length() > 8 * ln and delta > 0:
+                        kv >>= delta
+                    kb[j] = np.frombuffer(kv.to_bytes(ln, "big"), np.uint8)
+                es, ds = np.ascontiguousarray(e[todo]), np.ascontiguousarray(d[todo])
+                rr = np.zeros((len(todo), ln), np.uint8); ss = np.zeros((len(todo), ln), np.uint8)
+                cc = np.zeros(len(todo), np.uint8); tt = np.zeros(len(todo), np.uint8)
+                nat.check(lib.eb200_ecdsa_sign_batch_k(self._c["id"], len(todo), es.ctypes.data, ds.ctypes.data, kb.ctypes.data, flags,
+                                                       rr.ctypes.data, ss.ctypes.data, cc.ctypes.data, tt.ctypes.data))
+                ok = tt == nat.ST_TRUE
+                r[todo[ok]], s[todo[ok]], rec[todo[ok]], st[todo[ok]] = rr[ok], ss[ok], cc[ok], tt[ok]
+                if not bool(((tt == nat.ST_TRUE) | (tt == nat.ST_RETRY)).all()):
+                    raise nat.NativeError("sign_batch: unexpected status")
+                todo = todo[~ok]
+                if not len(todo):
+                    break
+        elif pers is not None:
+            pb = np.frombuffer(bytes(_to_array(pers, pers_enc or "utf8")) + b"\x00", np.uint8)
+            nat.check(lib.eb200_ecdsa_sign_batch_pers(self._c["id"], n, e.ctypes.data, d.ctypes.data, pb.ctypes.data, pb.size - 1, flags,
+                                                      r.ctypes.data, s.ctypes.data, rec.ctypes.data, st.ctypes.data))
+        else:
+            nat.check(lib.eb200_ecdsa_sign_batch(self._c["id"], n, e.ctypes.data, d.ctypes.data, flags,
+                                                 r.ctypes.data, s.ctypes.data, rec.ctypes.data, st.ctypes.data))
+        if not bool((st == nat.ST_TRUE).all()):
+            bad = int(np.flatnonzero(st != nat.ST_TRUE)[0])
+            raise nat.NativeError("sign_batch: item %d returned status %d" % (bad, int(st[bad])))
         return ([int.from_bytes(r[i].tobytes(), "big") for i in range(n)],
                 [int.from_bytes(s[i].tobytes(), "big") for i in range(n)], rec)
 
-    def sign(self, msg, priv, canonical=False):
-        r, s, rec = self.sign_batch([msg], [priv], canonical)
+    def gen_key_pair_batch(self, entropies, entropy_enc=None, pers=None, pers_enc=None):
+        """Batch of EC.prototype.genKeyPair({entropy, entropyEnc, pers, persEnc}) (ec/index.js:55-79): every item's key
+        comes from its own HMAC-DRBG(hash, entropy, nonce = n, pers).  All entropies must have the same byte length
+        (>= 24, the reference's 'Not enough entropy' assertion).  Returns (private keys, public points (x, y))."""
+        if self.name not in _XY:
+            raise EllipticError("gen_key_pair_batch: not available on " + self.name)
+        lib = nat.init(self._device)
+        ents = [bytes(_to_array(x, entropy_enc or "utf8")) for x in entropies]
+        n, ln = len(ents), self._len
+        if not n:
+            return [], []
+        ne = len(ents[0])
+        if any(len(x) < 24 for x in ents):
+            raise EllipticError("Not enough entropy. Minimum is: 192 bits")     # hmac-drbg ctor, dist:8708-8710
+        if any(len(x) != ne for x in ents):
+            raise EllipticError("gen_key_pair_batch: entropies of one batch must have the same length")
+        eb = np.frombuffer(b"".join(ents), np.uint8).reshape(n, ne)
+        pb = np.frombuffer(bytes(_to_array(pers, pers_enc or "utf8")) + b"\x00", np.uint8) if pers is not None else None
+        priv = np.zeros((n, ln), np.uint8); pub = np.zeros((n, 2 * ln), np.uint8); st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_ec_keygen_batch(self._c["id"], n, eb.ctypes.data, ne, pb.ctypes.data if pb is not None else None,
+                                            (pb.size - 1) if pb is not None else 0, priv.ctypes.data, pub.ctypes.data, st.ctypes.data))
+        if not bool((st == nat.ST_TRUE).all()):
+            raise nat.NativeError("gen_key_pair_batch: unexpected status")
+        return ([int.from_bytes(priv[i].tobytes(), "big") for i in range(n)],
+                [(int.from_bytes(pub[i, :ln].tobytes(), "big"), int.from_bytes(pub[i, ln:].tobytes(), "big")) for i in range(n)])
+
+    def sign(self, msg, priv, canonical=False, pers=None, pers_enc=None, k=None):
+        """EC.prototype.sign (ec/index.js:110-186); k: the reference's options.k(iter)."""
+        r, s, rec = self.sign_batch([msg], [priv], canonical, None, pers, pers_enc, (lambda i, it: k(it)) if k else None)
         return {"r": r[0], "s": s[0], "recoveryParam": int(rec[0])}
 
     # ---- public-key recovery -----------------------------------------------------------------------------
@@ -380,8 +465,10 @@ class EC:
         return out
 
     def _mul_common(self, k1, k2, pts):
-        if self.name not in _SHORT:
-            raise EllipticError("mul/mulAdd batches: short curves only")
+        if self.name == "curve25519":
+            raise EllipticError("Not supported on Montgomery curve")      # mont.js: mulAdd / jumlAdd throw; mul: x_mul_batch
+        if self.name not in _XY:
+            raise EllipticError("mul/mulAdd batches: not available on " + self.name)
         lib = nat.init(self._device)
         n, ln = len(k2), self._len
         out = np.zeros((n, 2 * ln), np.uint8)
@@ -392,8 +479,27 @@ class EC:
         else:
             nat.check(lib.eb200_mul_add_batch(self._c["id"], n, k1.ctypes.data, k2.ctypes.data, pts.ctypes.data,
                                               out.ctypes.data, st.ctypes.data))
+        if bool((st == nat.ST_NEEDS_HOST).any()):      # (only the Edwards preset reports it; the short curves replay)
+            raise NeedsReferencePath("point %d is not on the curve; the reference does not validate it" % int(np.flatnonzero(st == nat.ST_NEEDS_HOST)[0]))
         return [(int.from_bytes(out[i, :ln].tobytes(), "big"), int.from_bytes(out[i, ln:].tobytes(), "big"))
                 if st[i] == nat.ST_TRUE else None for i in range(n)]
+
+    def x_mul_batch(self, xs, ks):
+        """curve25519: [curve.point(x).mul(k).getX()] (mont.js:130-153, 173-178) -- x-only points, no validation."""
+        if self.name != "curve25519":
+            raise EllipticError("x_mul_batch: curve25519 only")
+        lib = nat.init(self._device)
+        n = len(ks)
+        kb = np.zeros((n, 32), np.uint8); xb = np.zeros((n, 32), np.uint8)
+        for i in range(n):
+            kv, xv = _bn(ks[i]), _bn(xs[i])
+            if kv >> 256:
+                raise NeedsReferencePath("scalar wider than 256 bits")
+            kb[i] = np.frombuffer(kv.to_bytes(32, "big"), np.uint8)
+            xb[i] = np.frombuffer((xv % self._c["p"] if xv >> 256 else xv).to_bytes(32, "big"), np.uint8)
+        out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
+        nat.check(lib.eb200_x25519_mul_batch(n, kb.ctypes.data, xb.ctypes.data, out.ctypes.data, st.ctypes.data))
+        return [int.from_bytes(out[i].tobytes(), "big") for i in range(n)]
 
     def g_mul_batch(self, ks):
         """[G.mul(k) for k in ks] (short.js:422-427, the keygen product ec/key.js:55-60): (x, y) or None = infinity."""

@@ -101,6 +101,53 @@ class EDDSA:
             h[i] = np.frombuffer(self.hash_int(sig[:32], pub, msg).to_bytes(32, "little"), np.uint8)
         return self.verify_batch_packed(R, S, A, h)
 
+    def sign_batch_packed(self, secrets, msgs, msg_off, want_pub=False):
+        """secrets: (n, 32) uint8; msgs: concatenated message bytes; msg_off: n + 1 uint64 offsets.
+        Returns the (n, 64) signatures Rencoded || S (and the (n, 32) public keys with want_pub)."""
+        lib = nat.init(self._device)
+        secrets = np.ascontiguousarray(secrets, dtype=np.uint8)
+        msgs = np.ascontiguousarray(msgs, dtype=np.uint8)
+        msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
+        n = secrets.shape[0]
+        if secrets.shape != (n, 32) or msg_off.shape != (n + 1,) or int(msg_off[n]) != msgs.size:
+            raise EllipticError("sign_batch_packed: secrets (n, 32), n + 1 offsets covering msgs expected")
+        sig = np.empty((n, 64), np.uint8)
+        pub = np.empty((n, 32), np.uint8) if want_pub else None
+        st = np.empty(n, np.uint8)
+        nat.check(lib.eb200_eddsa_sign_batch(n, secrets.ctypes.data, msgs.ctypes.data if msgs.size else None, msg_off.ctypes.data,
+                                             sig.ctypes.data, pub.ctypes.data if want_pub else None, st.ctypes.data))
+        if not bool((st == nat.ST_TRUE).all()):
+            raise nat.NativeError("eddsa sign: unexpected status")
+        return (sig, pub) if want_pub else sig
+
+    def sign_batch(self, messages, secrets):
+        """EDDSA#signBatch: lists of the reference's own argument forms (hex strings / byte arrays); secrets as
+        eddsa.keyFromSecret takes them.  Returns a list of 64-byte signatures (sig.toBytes())."""
+        n = len(messages)
+        sec = np.zeros((n, 32), np.uint8)
+        ms = []
+        for i in range(n):
+            sk = _parse_bytes(secrets[i])
+            if len(sk) != 32:
+                raise EllipticError("unsupported secret length %d" % len(sk))
+            sec[i] = np.frombuffer(bytes(sk), np.uint8)
+            ms.append(bytes(_parse_bytes(messages[i])))
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum([len(m) for m in ms])
+        sig = self.sign_batch_packed(sec, np.frombuffer(b"".join(ms), np.uint8), off)
+        return [sig[i].tobytes() for i in range(n)]
+
+    def sign(self, message, secret):
+        """EDDSA.prototype.sign (eddsa/index.js:34-44): the 64 signature bytes (sig.toBytes())."""
+        return self.sign_batch([message], [secret])[0]
+
+    def public_from_secret_batch(self, secrets):
+        """key.getPublic('bytes') for a batch of secrets (a fixed-base multiplication each)."""
+        secrets = np.ascontiguousarray(secrets, dtype=np.uint8)
+        n = secrets.shape[0]
+        _, pub = self.sign_batch_packed(secrets, np.zeros(0, np.uint8), np.zeros(n + 1, np.uint64), want_pub=True)
+        return pub
+
     def verify(self, message, sig, pub):
         """EDDSA.prototype.verify (eddsa/index.js:52-63): bool, or raises."""
         st = int(self.verify_batch([message], [sig], [pub])[0])

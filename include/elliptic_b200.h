@@ -44,6 +44,8 @@ extern "C" {
 #define EB200_ST_INFINITY 7             /* (recover) returned the point at infinity */
 #define EB200_ST_THROW_SECOND_KEY 8     /* (recover) threw Error('Unable to find sencond key candinate')  ec/index.js:244 */
 #define EB200_ST_THROW_SIG_FORMAT 9     /* threw Error('Signature without r or s')  ec/signature.js:15 (DER rejected by _importDER) */
+#define EB200_ST_RETRY 10               /* (sign with caller nonces) the reference's loop `continue`s: k outside [2, n-2], r = 0 or s = 0;
+                                           the caller supplies its next k(iter), ec/index.js:153-185 */
 
 /* curve ids (names of lib/elliptic/curves.js presets) */
 #define EB200_CURVE_SECP256K1 1
@@ -69,9 +71,17 @@ typedef struct eb200_timing {
   uint32_t launches; /* kernels launched by the last call */
 } eb200_timing;
 
-/* Select device `device` (CUDA ordinal), build the fixed-base tables.  Idempotent per device. */
-int eb200_init(int device);
+/* Create (or keep) one context per listed CUDA ordinal and build the fixed-base tables there
+ * (eb200_init(devices[], ndev, flags)).  devices == NULL or ndev <= 0: every visible device.
+ * Idempotent per device; later calls add devices.  Host-pointer entry points split a batch into contiguous
+ * blocks over the initialised devices (no exchange between blocks) when it has at least 2^14 items per
+ * device, each block driven by its own host thread; smaller calls take one device, rotating, so that concurrent
+ * callers spread out.  Device-pointer (`_dev`) entry points run on the device that owns `d_status`.
+ * Every entry point is safe to call from several threads. */
+#define EB200_INIT_ALL_TABLES 1u   /* build every curve's fixed-base table now instead of on first use */
+int eb200_init(const int* devices, int ndev, uint32_t flags);
 int eb200_shutdown(void);
+int eb200_device_count(void);          /* devices initialised so far */
 const char* eb200_strerror(int code);
 const char* eb200_last_error(void);   /* text of the last CUDA error on this thread's context */
 int eb200_last_timing(eb200_timing* out);
@@ -82,7 +92,8 @@ int eb200_last_timing(eb200_timing* out);
  *   r,s : n x len  signature halves (Signature{r,s}, ec/signature.js:8-22)
  *   pub : n x (pub_fmt-dependent) public keys
  *   status : n bytes out
- * Host pointers; copies are done internally on the library's stream. */
+ * Host pointers (pinned or pageable: pageable buffers are staged through an internal pinned ring with a
+ * parallel memcpy, so an unpinned caller such as a Node.js Buffer gets the pinned transfer rate); copies are done internally on the library's stream. */
 int eb200_ecdsa_verify_batch(int curve, size_t n, const uint8_t* e, const uint8_t* r,
                              const uint8_t* s, const uint8_t* pub, uint32_t pub_fmt,
                              uint8_t* status);
@@ -179,6 +190,63 @@ int eb200_eddsa_verify_batch_dev(size_t n, const uint8_t* d_R, const uint8_t* d_
 int eb200_x25519_derive_batch(size_t n, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status);
 int eb200_x25519_derive_batch_dev(size_t n, const uint8_t* d_priv, const uint8_t* d_pubx, uint8_t* d_out,
                                   uint8_t* d_status, void* stream);
+
+/* EC.prototype.sign with the `k` option (options.k(iter), lib/elliptic/ec/index.js:154-157): one attempt of the
+ * reference's loop with the caller's nonces.  k: n x len bytes big-endian, what k(iter) returned (it goes through
+ * _truncateToN(k, true) here).  status: EB200_ST_TRUE, or EB200_ST_RETRY where the reference would call k(iter + 1). */
+int eb200_ecdsa_sign_batch_k(int curve, size_t n, const uint8_t* e, const uint8_t* priv, const uint8_t* k, uint32_t flags,
+                             uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status);
+/* EC.prototype.sign with the `pers` option (ec/index.js:143-151): HMAC-DRBG seeded with key || msg || pers; pers is the
+ * personalisation string after `persEnc` decoding, shared by the whole batch. */
+int eb200_ecdsa_sign_batch_pers(int curve, size_t n, const uint8_t* e, const uint8_t* priv, const uint8_t* pers, size_t pers_len,
+                                uint32_t flags, uint8_t* out_r, uint8_t* out_s, uint8_t* out_recid, uint8_t* status);
+/* EC.prototype.genKeyPair({entropy, pers}) (ec/index.js:55-79): per item HMAC-DRBG(hash, entropy_i, nonce = n.toArray(),
+ * pers), the first candidate <= n - 2 plus one as the private key, and its public point.
+ *   entropy : n x entropy_len bytes (the reference requires >= hmacStrength / 8 = 24);  out_priv : n x len;
+ *   out_pub_xy : n x 2 len or NULL */
+int eb200_ec_keygen_batch(int curve, size_t n, const uint8_t* entropy, size_t entropy_len, const uint8_t* pers, size_t pers_len,
+                          uint8_t* out_priv, uint8_t* out_pub_xy, uint8_t* status);
+
+/* The `ec` / `.curve` API over the other two curve types of lib/elliptic/curves.js:
+ *  - EB200_CURVE_ED25519 is accepted by eb200_ecdsa_verify_batch (+ _der, SEC1 formats: BaseCurve.decodePoint and
+ *    EdwardsCurve.pointFromX, edwards.js:46-69), eb200_ecdsa_sign_batch (+ _k, _pers), eb200_ec_keygen_batch,
+ *    eb200_scalar_mul_batch / eb200_mul_add_batch (Point.mul / mulAdd, edwards.js:362-375; 32-byte big-endian x || y,
+ *    the neutral element is the ordinary point (0, 1)) and eb200_ecdh_derive_batch: new elliptic.ec('ed25519')
+ *    (test/ecdsa-test.js:130, test/ecdh-test.js:26; eqXToP edwards.js:415-431).  An un-validated off-curve point is
+ *    reported as EB200_ST_NEEDS_HOST (the reference's answer then depends on its own wNAF schedule, which is not
+ *    replayed for this curve); eb200_ecdsa_recover_batch returns EB200_ERR_UNSUPPORTED.
+ *  - curve25519 points are x-only: eb200_x25519_mul_batch is MontCurve Point.mul(k).getX() (mont.js:130-153) without
+ *    the validation that eb200_x25519_derive_batch (KeyPair.derive) performs; mulAdd throws in the reference. */
+int eb200_x25519_mul_batch(size_t n, const uint8_t* k, const uint8_t* px, uint8_t* out_x, uint8_t* status);
+
+/* Short Weierstrass curves given at run time -- the batch form of `new elliptic.curve.short({p, a, b})`
+ * (lib/elliptic/curve/short.js:10-24) and of Point.mul / mulAdd / add / dbl / validate on its points
+ * (short.js:365-450, 206-216).  p: any odd prime > 3 of up to 576 bits; p, a, b: `len` bytes big-endian; points:
+ * x || y, `len` bytes each (values >= p are reduced on entry like toRed); scalars: `klen` bytes big-endian, any value.
+ * status: EB200_ST_TRUE = affine point written, EB200_ST_INFINITY = the point at infinity (output zeroed),
+ * EB200_ST_NEEDS_HOST = an input does not satisfy the curve equation (the reference does not validate and its result
+ * is then an artefact of its own schedule: not accelerated); validate: EB200_ST_TRUE / EB200_ST_FALSE.
+ * The six presets keep their tuned entry points above; this generic path is not tuned (one thread per item,
+ * double-and-add). */
+typedef struct eb200_short_curve { uint32_t len; const uint8_t* p; const uint8_t* a; const uint8_t* b; } eb200_short_curve;
+int eb200_curve_mul_batch(const eb200_short_curve* curve, size_t n, const uint8_t* k, size_t klen, const uint8_t* points_xy,
+                          uint8_t* out_xy, uint8_t* status);
+int eb200_curve_mul_add_batch(const eb200_short_curve* curve, size_t n, const uint8_t* k1, const uint8_t* p1_xy, const uint8_t* k2,
+                              const uint8_t* p2_xy, size_t klen, uint8_t* out_xy, uint8_t* status);
+int eb200_curve_add_batch(const eb200_short_curve* curve, size_t n, const uint8_t* p1_xy, const uint8_t* p2_xy, uint8_t* out_xy,
+                          uint8_t* status);
+int eb200_curve_dbl_batch(const eb200_short_curve* curve, size_t n, const uint8_t* p_xy, uint8_t* out_xy, uint8_t* status);
+int eb200_curve_validate_batch(const eb200_short_curve* curve, size_t n, const uint8_t* p_xy, uint8_t* status);
+
+/* Batch of EDDSA.prototype.sign (lib/elliptic/eddsa/index.js:34-44) with keys given as 32-byte secrets
+ * (eddsa.keyFromSecret, eddsa/key.js:52-75: SHA-512 of the secret, clamped scalar, message prefix).
+ *   secrets : n x 32 bytes;  msgs / msg_off : concatenated raw messages and n + 1 offsets
+ *   out_sig : n x 64 bytes  Rencoded || S (little-endian), byte-identical to sig.toBytes()
+ *   out_pub : n x 32 bytes  key.getPublic('bytes'), or NULL
+ *   status  : n bytes, always EB200_ST_TRUE (the reference cannot fail on a 32-byte secret)
+ * Everything (three SHA-512 per item, two fixed-base multiplications, the arithmetic mod n) runs on the GPU. */
+int eb200_eddsa_sign_batch(size_t n, const uint8_t* secrets, const uint8_t* msgs, const uint64_t* msg_off,
+                           uint8_t* out_sig, uint8_t* out_pub, uint8_t* status);
 
 /* Self-test hooks used by the parity tests (device arithmetic vs the oracle).
  * op: 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 5 mul_small(b[0]), 6 normalize, 7 inv, 8 sqrt candidate.

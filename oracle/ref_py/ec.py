@@ -5,7 +5,7 @@ import hmac as _hmac
 
 from . import curves
 from .bn import RefError, ref_assert
-from .signature import Signature, _bn
+from .signature import Signature, _bn, _parse_hex
 from .utils import to_array
 
 
@@ -104,6 +104,20 @@ class EC:
     def key_from_public(self, pub, enc=None):
         return pub if isinstance(pub, KeyPair) else KeyPair(self, pub=pub, pub_enc=enc)
 
+    def gen_key_pair(self, entropy, pers=b""):
+        """ec/index.js:55-79 with options.entropy given (bytes, after entropyEnc decoding): HmacDRBG(hash, entropy,
+        nonce = n.toArray(), pers); first candidate priv <= n - 2, plus one."""
+        entropy = bytes(entropy)
+        ref_assert(len(entropy) >= 24, "Not enough entropy. Minimum is: 192 bits")     # hmac-drbg ctor, dist:8708-8710
+        nbytes = (self.n.bit_length() + 7) // 8
+        drbg = HmacDRBG(self.hash, entropy, self.n.to_bytes(nbytes, "big"), pers)
+        ns2 = self.n - 2
+        while True:
+            priv = int.from_bytes(drbg.generate(nbytes), "big")
+            if priv > ns2:
+                continue
+            return KeyPair(self, priv=priv + 1)
+
     def _truncate_to_n(self, msg, trunc_only=False, bit_length=None):
         """ec/index.js:81-108 (quirk Q3).  msg: int (BN), hex str or bytes."""
         if isinstance(msg, int):
@@ -111,7 +125,7 @@ class EC:
             byte_length = (v.bit_length() + 7) // 8
         elif isinstance(msg, str):
             byte_length = (len(msg) + 1) >> 1
-            v = int(msg, 16) if msg else 0
+            v = _parse_hex(msg)
         else:
             byte_length = len(msg)
             v = int.from_bytes(bytes(msg), "big")

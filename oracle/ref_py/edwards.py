@@ -202,6 +202,22 @@ class EdwardsCurve:
     def jpoint(self, x, y, z, t=None):
         return self.point(x, y, z, t)
 
+    def point_from_x(self, x, odd):
+        """edwards.js:46-69."""
+        red = self.red
+        x = red.conv(x)
+        x2 = red.sqr(x)
+        rhs = red.sub(self.c2, red.mul(self.a, x2))
+        lhs = red.sub(1, red.mul(red.mul(self.c2, self.d), x2))
+        y2 = red.mul(rhs, red.invm(lhs))
+        y = red.sqrt(y2)
+        if red.sub(red.sqr(y), y2) != 0:
+            raise RefError("invalid point")
+        is_odd = bool(y & 1)
+        if (odd and not is_odd) or (not odd and is_odd):
+            y = red.neg(y)
+        return self.point(x, y)
+
     def point_from_y(self, y, odd):
         """edwards.js:71-97."""
         red = self.red
@@ -234,6 +250,7 @@ class EdwardsCurve:
         return lhs == rhs
 
     from .short import ShortCurve as _S
+    decode_point = _S.decode_point          # BaseCurve.decodePoint (base.js:270-292) is shared by all curve types
     _fixed_naf_mul = _S._fixed_naf_mul
     _wnaf_mul = _S._wnaf_mul
     _wnaf_mul_add = _S._wnaf_mul_add

@@ -123,10 +123,30 @@ class Signature:
         return bytes(res + out)
 
 
+def _parse_hex(s):
+    """bn.js 4.11.9 `new BN(str, 16)` (dist/elliptic.js:4135-4157 parseHex, :4003-4017): whitespace is dropped, a
+    leading '-' negates, and a character outside [0-9a-fA-F] contributes (charCode - 48) & 0xf instead of throwing."""
+    s = "".join(s.split())
+    neg = s.startswith("-")
+    if neg:
+        s = s[1:]
+    v = 0
+    for ch in s:
+        c = ord(ch) - 48
+        if 49 <= c <= 54:
+            d = c - 49 + 10
+        elif 17 <= c <= 22:
+            d = c - 17 + 10
+        else:
+            d = c & 0xF
+        v = (v << 4) | d
+    return -v if neg else v
+
+
 def _bn(v):
     """new BN(v, 16) for the forms callers use: int (BN), hex str, byte array."""
     if isinstance(v, int):
         return v
     if isinstance(v, str):
-        return int(v, 16) if v else 0
+        return _parse_hex(v)
     return int.from_bytes(bytes(v), "big")

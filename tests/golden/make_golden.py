@@ -4,7 +4,7 @@
 Run in the build container (reads /root/reference, which does not exist on the GPU box):
     python tests/golden/make_golden.py
 Outputs (tests/golden/):
-    ed25519_sign_input.json.gz   test/fixtures/sign.input: first 128 lines + every 16th after
+    ed25519_sign_input.json.gz   test/fixtures/sign.input: all 1024 lines (secret, pk, msg, sig)
     ed25519_derivation.json      test/fixtures/derivation-fixtures.js (256 entries: secret, a, A, A_P)
     secp256k1_precomputed.json   digest + samples of lib/elliptic/precomputed/secp256k1.js
     ecdsa_kats.json              test/ecdsa-test.js: Maxwell vectors (:352-451), RFC 6979 (:135-350),
@@ -23,7 +23,7 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def sign_input():
     lines = open(os.path.join(REF, "test/fixtures/sign.input")).read().split("\n")
     lines = [l for l in lines if l]
-    keep = list(range(128)) + list(range(128, len(lines), 16))
+    keep = list(range(len(lines)))          # all 1024: EdDSA sign / verify KATs with message lengths 0..1023
     out = []
     for i in keep:
         sk_pk, pk, msg, sig_msg, _ = lines[i].split(":")

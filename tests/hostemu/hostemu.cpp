@@ -110,7 +110,7 @@ extern "C" void he_sw_verify(int curve, size_t N, const uint8_t* e, const uint8_
 // ---------------------------------------------------------------------------
 // ed25519 verify / curve25519 derive through the same bodies
 #include "../../elliptic_b200/csrc/ed25519_body.cuh"
-extern "C" void he_ed25519_verify(size_t N, const uint8_t* R, const uint8_t* S, const uint8_t* A, const uint8_t* h, uint8_t* status) {
+static const std::vector<u32>& ed_host_gtab() {
   static std::vector<u32> gtab;
   if (gtab.empty()) {
     gtab.resize((size_t)ED_GWINDOWS * ED_GENTRIES * 24);
@@ -132,8 +132,16 @@ extern "C" void he_ed25519_verify(size_t N, const uint8_t* R, const uint8_t* S, 
       for (int k = 0; k < ED_GW; k++) base = ed_dbl(base);
     }
   }
+  return gtab;
+}
+extern "C" void he_ed25519_verify(size_t N, const uint8_t* R, const uint8_t* S, const uint8_t* A, const uint8_t* h, uint8_t* status) {
+  const std::vector<u32>& gtab = ed_host_gtab();
   std::vector<u32> atab((size_t)ED_ATAB_WORDS * N);
   for (size_t i = 0; i < N; i++) status[i] = ed25519_verify_item(i, R, S, A, h, gtab.data(), atab.data());
+}
+extern "C" void he_ed25519_sign(size_t N, const uint8_t* secrets, const uint8_t* msgs, const u64* off, uint8_t* sig, uint8_t* pub) {
+  const std::vector<u32>& gtab = ed_host_gtab();
+  for (size_t i = 0; i < N; i++) ed25519_sign_item(i, secrets, msgs, off, gtab.data(), sig, pub);
 }
 extern "C" void he_x25519_derive(size_t N, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status) {
   for (size_t i = 0; i < N; i++) status[i] = x25519_derive_item(i, priv, pubx, out);
@@ -431,4 +439,124 @@ extern "C" int he_sw_sqrt(int curve, const u32* a, u32* out) {
   if (curve == 7) return sw_sqrt_host<P192>(a, out);
   if (curve == 8) return sw_sqrt_host<P224>(a, out);
   return sw_sqrt_host<P384>(a, out);
+}
+
+// Coordinate-field operations of a short curve on plain integers (to_mont / op / from_mont):
+// op 0 mul, 1 sqr, 2 add, 3 sub, 4 neg, 6 reduce (toRed), 7 inv.  a, b, out: C::N words.
+template <class C>
+static void sw_fe_op_t(int op, const u32* a, const u32* b, u32* out) {
+  typedef typename SW<C>::F F;
+  constexpr int NL = C::N;
+  typename F::fe A = F::to_mont(load_fe_n<NL>(a)), B = F::to_mont(load_fe_n<NL>(b)), R;
+  switch (op) {
+    case 0: R = F::mul(A, B); break;
+    case 1: R = F::sqr(A); break;
+    case 2: R = F::add(A, B); break;
+    case 3: R = F::sub(A, B); break;
+    case 4: R = F::neg(A); break;
+    case 7: R = F::inv(A); break;
+    default: R = A;
+  }
+  store_fe_n<NL>(out, F::from_mont(R));
+}
+extern "C" void he_sw_fe_op(int curve, int op, const u32* a, const u32* b, u32* out) {
+  switch (curve) {
+    case 2: sw_fe_op_t<P256>(op, a, b, out); break;
+    case 3: sw_fe_op_t<P384>(op, a, b, out); break;
+    case 6: sw_fe_op_t<P521>(op, a, b, out); break;
+    case 7: sw_fe_op_t<P192>(op, a, b, out); break;
+    default: sw_fe_op_t<P224>(op, a, b, out);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// EC.sign options (k, pers) and EC.genKeyPair({entropy, pers}) through the kernel bodies.
+// mode 0: caller nonces kgiven (one attempt; 10 = the reference would ask for k(iter + 1)), mode 1: pers
+template <class SG, class C>
+static void sw_sign_opt_host(int mode, size_t N, const uint8_t* e, const uint8_t* priv, const uint8_t* kgiven, const uint8_t* pers, int np,
+                             u32 canonical, uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status) {
+  typedef SW<C> W;
+  static std::vector<u32> gtab;
+  if (gtab.empty()) {
+    gtab.resize((size_t)W::GWINDOWS * W::GENTRIES * 2 * W::N);
+    for (int j = 0; j < W::GWINDOWS; j++)
+      for (int i = 0; i < W::GENTRIES; i++) W::gtab_entry(j, i, &gtab[((size_t)j * W::GENTRIES + i) * 2 * W::N]);
+  }
+  if (mode == 1) {
+    for (size_t i = 0; i < N; i++) status[i] = SG::slow_item_pers(i, e, priv, pers, np, canonical, gtab.data(), r, s, recid);
+    return;
+  }
+  std::vector<u32> ws((size_t)SG::WS_WORDS * N), scratch((size_t)SG::SCRATCH_WORDS * N);
+  for (size_t i = 0; i < N; i++) SG::nonce_item(i, N, e, priv, gtab.data(), ws.data(), status, kgiven);
+  size_t T = (N + SG::BATCH - 1) / SG::BATCH;
+  for (size_t t = 0; t < T; t++) SG::finish_thread(t, T, N, e, priv, canonical, ws.data(), scratch.data(), r, s, recid, status);
+  for (size_t i = 0; i < N; i++) if (status[i] == 4) status[i] = 10;
+}
+extern "C" void he_sign_opt(int curve, int mode, size_t N, const uint8_t* e, const uint8_t* priv, const uint8_t* kgiven, const uint8_t* pers,
+                            int np, u32 canonical, const u32* k256_gtab, uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status) {
+  if (curve == 1) {
+    if (mode == 1) { for (size_t i = 0; i < N; i++) status[i] = k256_sign_item_pers(i, e, priv, pers, np, canonical, k256_gtab, r, s, recid); return; }
+    std::vector<u32> ws((size_t)SIGN_WS_WORDS * N), scratch((size_t)SIGN_SCRATCH_WORDS * N);
+    for (size_t i = 0; i < N; i++) k256_sign_nonce_item(i, N, e, priv, k256_gtab, ws.data(), status, kgiven);
+    size_t T = (N + PREP_BATCH - 1) / PREP_BATCH;
+    for (size_t t = 0; t < T; t++) k256_sign_finish_thread(t, T, N, e, priv, canonical, ws.data(), scratch.data(), r, s, recid, status);
+    for (size_t i = 0; i < N; i++) if (status[i] == ST_NEEDS_HOST) status[i] = 10;
+  }
+  else if (curve == 2) sw_sign_opt_host<SWSign<P256, Sha256W>, P256>(mode, N, e, priv, kgiven, pers, np, canonical, r, s, recid, status);
+  else if (curve == 3) sw_sign_opt_host<SWSign<P384, Sha384W>, P384>(mode, N, e, priv, kgiven, pers, np, canonical, r, s, recid, status);
+  else if (curve == 6) sw_sign_opt_host<SWSign<P521, Sha512W>, P521>(mode, N, e, priv, kgiven, pers, np, canonical, r, s, recid, status);
+  else if (curve == 7) sw_sign_opt_host<SWSign<P192, Sha256W>, P192>(mode, N, e, priv, kgiven, pers, np, canonical, r, s, recid, status);
+  else sw_sign_opt_host<SWSign<P224, Sha256W>, P224>(mode, N, e, priv, kgiven, pers, np, canonical, r, s, recid, status);
+}
+extern "C" void he_keygen(int curve, size_t N, const uint8_t* entropy, int ne, const uint8_t* pers, int np, uint8_t* out_priv, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) {
+    if (curve == 1) status[i] = k256_keygen_item(i, entropy, ne, pers, np, out_priv);
+    else if (curve == 2) status[i] = SWSign<P256, Sha256W>::keygen_item(i, entropy, ne, pers, np, out_priv);
+    else if (curve == 3) status[i] = SWSign<P384, Sha384W>::keygen_item(i, entropy, ne, pers, np, out_priv);
+    else if (curve == 6) status[i] = SWSign<P521, Sha512W>::keygen_item(i, entropy, ne, pers, np, out_priv);
+    else if (curve == 7) status[i] = SWSign<P192, Sha256W>::keygen_item(i, entropy, ne, pers, np, out_priv);
+    else status[i] = SWSign<P224, Sha256W>::keygen_item(i, entropy, ne, pers, np, out_priv);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the `ec` API over ed25519 (ed25519_ec.cuh)
+#include "../../elliptic_b200/csrc/ed25519_ec.cuh"
+extern "C" void he_ed_ec_verify(size_t N, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub, int fmt, uint8_t* status) {
+  const std::vector<u32>& gtab = ed_host_gtab();
+  std::vector<u32> atab((size_t)ED_ATAB_WORDS * N);
+  std::vector<uint8_t> xy(64 * N), pre(N, 0);
+  const uint8_t* pxy = pub;
+  if (fmt) {
+    for (size_t i = 0; i < N; i++) pre[i] = ed_ec_decode_pub(pub + (fmt == 1 ? 65 : 33) * i, (u32)fmt, xy.data() + 64 * i);
+    pxy = xy.data();
+  }
+  for (size_t i = 0; i < N; i++) status[i] = ed_ec_verify_item(i, e, r, s, pxy, fmt ? pre.data() : nullptr, gtab.data(), atab.data());
+}
+extern "C" void he_ed_ec_sign(size_t N, const uint8_t* e, const uint8_t* priv, const uint8_t* kgiven, const uint8_t* pers, int np,
+                              u32 canonical, uint8_t* r, uint8_t* s, uint8_t* recid, uint8_t* status) {
+  const std::vector<u32>& gtab = ed_host_gtab();
+  for (size_t i = 0; i < N; i++) status[i] = ed_ec_sign_item(i, e, priv, kgiven, pers, np, canonical, gtab.data(), r, s, recid);
+}
+extern "C" void he_ed_ec_keygen(size_t N, const uint8_t* entropy, int ne, const uint8_t* pers, int np, uint8_t* out_priv, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = ed_ec_keygen_item(i, entropy, ne, pers, np, out_priv);
+}
+extern "C" void he_ed_ec_mul_add(size_t N, const uint8_t* k1, const uint8_t* k2, const uint8_t* pts, int derive, uint8_t* out, uint8_t* status) {
+  const std::vector<u32>& gtab = ed_host_gtab();
+  std::vector<u32> atab((size_t)ED_ATAB_WORDS * N);
+  for (size_t i = 0; i < N; i++) status[i] = ed_ec_mul_add_item(i, k1, k2, pts, derive != 0, gtab.data(), atab.data(), out);
+}
+extern "C" void he_x25519_mul(size_t N, const uint8_t* k, const uint8_t* px, uint8_t* out, uint8_t* status) {
+  for (size_t i = 0; i < N; i++) status[i] = x25519_mul_item(i, k, px, out);
+}
+
+// ---------------------------------------------------------------------------
+// run-time short curves (sw_runtime.cuh): the host fills the parameter block exactly like rt_make in eb200.cu
+#include "../../elliptic_b200/csrc/sw_runtime.cuh"
+extern "C" void he_rt_item(int op, const u32* p8, const u32* r1, const u32* r2, const u32* a_m, const u32* b_m, u32 n0inv, u32 len,
+                           const uint8_t* k1, const uint8_t* p1, const uint8_t* k2, const uint8_t* p2, u32 klen, uint8_t* out, uint8_t* status) {
+  RtCurve<8> C;
+  for (int i = 0; i < 8; i++) { C.p[i] = p8[i]; C.r1[i] = r1[i]; C.r2[i] = r2[i]; C.a[i] = a_m[i]; C.b[i] = b_m[i]; }
+  C.n0inv = n0inv; C.len = len; C.a_is_zero = 0;
+  status[0] = RtG<8>::item(op, 0, k1, p1, k2, p2, klen, out, C);
 }

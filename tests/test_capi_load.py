@@ -25,7 +25,10 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a GPU is present")
     from elliptic_b200 import _native
     lib = _native.load()
-    assert lib.eb200_init(0) == _native.ERR_NO_DEVICE
+    import ctypes
+    dev0 = (ctypes.c_int * 1)(0)
+    assert lib.eb200_init(dev0, 1, 0) == _native.ERR_NO_DEVICE
+    assert lib.eb200_init(None, 0, 0) == _native.ERR_NO_DEVICE and lib.eb200_device_count() == 0
     import numpy as np
     from elliptic_b200.ec import EC
     z = np.zeros((1, 32), np.uint8)
@@ -38,10 +41,15 @@ def test_product_package_does_not_import_the_oracle():
     import sys
     code = "import sys; import elliptic_b200, elliptic_b200.ec; assert not [m for m in sys.modules if m.startswith('oracle')]"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
-    for dirpath, _, files in os.walk(os.path.join(ROOT, "elliptic_b200")):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("the oracle", "").replace("oracle/", "").lower() or True
+    # no product source file imports, includes or links anything under oracle/ (comments may mention the oracle)
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#\s*include\s+[\"<][^\">]*oracle)", re.M)
+    for top in ("elliptic_b200", "include", "binding"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".js", ".inc")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not pat.search(src), os.path.join(dirpath, f)
+                    assert "libk256_ref" not in src and "c_oracle" not in src, os.path.join(dirpath, f)
 
 
 def test_host_side_parsing_matches_reference_forms():
@@ -64,3 +72,23 @@ def test_host_side_parsing_matches_reference_forms():
         assert ec._truncate_to_n(m) == ref._truncate_to_n(m)
     with pytest.raises(EllipticError):
         ec._public("05" + "00" * 32, "hex")
+
+
+def test_napi_shim_compiles_against_the_header():
+    """binding/elliptic_b200_napi.c (the N-API addon a Node.js maintainer builds) must stay in step with
+    include/elliptic_b200.h: compile it (no Node.js here: against binding/node_api_min.h) with warnings as errors,
+    and check that it binds every host-pointer batch entry point of the header."""
+    import subprocess
+    src = os.path.join(ROOT, "binding", "elliptic_b200_napi.c")
+    subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "binding"),
+                    "-I" + os.path.join(ROOT, "include"), src], check=True)
+    code = open(src).read()
+    hdr = open(os.path.join(ROOT, "include", "elliptic_b200.h")).read()
+    declared = set(re.findall(r"\b(eb200_\w+)\s*\(", hdr))
+    not_for_js = {n for n in declared if n.endswith("_dev") or n.startswith("eb200_selftest") or n.endswith("workspace_bytes")}
+    not_for_js |= {"eb200_shutdown", "eb200_device_count", "eb200_last_timing"}
+    missing = sorted(n for n in declared - not_for_js if n + "(" not in code)
+    assert not missing, missing
+    js = open(os.path.join(ROOT, "binding", "index.js")).read()
+    for name in re.findall(r'\{"(\w+)", \w+\}', code):
+        assert name == "init" or ("native." + name) in js, name       # every addon function is reachable from the JS wrapper

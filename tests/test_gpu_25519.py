@@ -38,6 +38,53 @@ def test_ed25519_reference_argument_forms(native):
         ged.verify(v["msg"], v["sig"], "02" + "00" * 31)
 
 
+def test_eddsa_sign_all_1024_sign_input_kats(native):
+    """EDDSA.sign on the GPU (eddsa/index.js:34-44): byte-identical signatures and public keys for all 1024 lines
+    of the reference's test/fixtures/sign.input (test/ed25519-test.js:44-85), then every one of them verifies and
+    every forged message does not."""
+    import gzip, json, os
+    from elliptic_b200.eddsa import EDDSA as GpuEd
+    data = json.load(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "ed25519_sign_input.json.gz"), "rt"))
+    vecs = data["vectors"]
+    assert len(vecs) == 1024
+    ged = GpuEd()
+    sigs = ged.sign_batch([v["msg"] for v in vecs], [v["secret"] for v in vecs])
+    assert [s.hex() for s in sigs] == [v["sig"] for v in vecs]
+    sec = np.frombuffer(b"".join(bytes.fromhex(v["secret"]) for v in vecs), np.uint8).reshape(-1, 32)
+    pubs = ged.public_from_secret_batch(sec)
+    assert [pubs[i].tobytes().hex() for i in range(1024)] == [v["pk"] for v in vecs]
+    msgs = [bytes.fromhex(v["msg"]) for v in vecs]
+    assert (ged.verify_batch(msgs, sigs, [bytes.fromhex(v["pk"]) for v in vecs]) == 1).all()
+    forged = [(m[:-1] + bytes([(m[-1] + 1) & 255])) if m else b"x" for m in msgs]
+    assert (ged.verify_batch(forged, sigs, [bytes.fromhex(v["pk"]) for v in vecs]) == 0).all()
+    # single-item reference forms
+    assert ged.sign(vecs[7]["msg"], vecs[7]["secret"]).hex() == vecs[7]["sig"]
+    assert ged.sign(list(bytes.fromhex(vecs[9]["msg"])), list(bytes.fromhex(vecs[9]["secret"]))).hex() == vecs[9]["sig"]
+
+
+def test_eddsa_sign_verify_round_trip_2e18(native):
+    """2^18 random secrets and 32-byte messages: sign on the GPU, verify on the GPU, libsodium agrees on a sample."""
+    import nacl.signing
+    from elliptic_b200.eddsa import EDDSA as GpuEd
+    n = 1 << 18
+    rng = np.random.default_rng(33)
+    sec = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    off = np.arange(n + 1, dtype=np.uint64) * 32
+    ged = GpuEd()
+    sig, pub = ged.sign_batch_packed(sec, msgs.reshape(-1), off, want_pub=True)
+    st = ged.verify_batch_msgs_packed(sig[:, :32].copy(), sig[:, 32:].copy(), pub, msgs.reshape(-1), off)
+    assert (st == 1).all()
+    msgs[:, 5] ^= 1
+    st = ged.verify_batch_msgs_packed(sig[:, :32].copy(), sig[:, 32:].copy(), pub, msgs.reshape(-1), off)
+    assert (st == 0).all()
+    msgs[:, 5] ^= 1
+    for i in range(0, n, n // 64):
+        k = nacl.signing.SigningKey(sec[i].tobytes())
+        assert bytes(k.verify_key) == pub[i].tobytes()
+        assert k.sign(msgs[i].tobytes()).signature == sig[i].tobytes()
+
+
 def test_curve25519_derive_parity(native):
     from elliptic_b200.ec import EC as GpuEC
     from elliptic_b200 import _native as nat

@@ -188,7 +188,7 @@ def test_c_abi_argument_and_error_behaviour(native):
     assert lib.eb200_ecdsa_verify_batch(77, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 0, st.ctypes.data) == -5  # UNSUPPORTED
     assert lib.eb200_ecdsa_verify_batch(1, 4, z.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data, 9, st.ctypes.data) == -5
     assert (st == 0xEE).all()
-    assert lib.eb200_ecdsa_sign_batch(4, 4, z.ctypes.data, z.ctypes.data, 0, z.ctypes.data, z.ctypes.data, st.ctypes.data, st.ctypes.data) == -5
+    assert lib.eb200_ecdsa_sign_batch(5, 4, z.ctypes.data, z.ctypes.data, 0, z.ctypes.data, z.ctypes.data, st.ctypes.data, st.ctypes.data) == -5
     assert lib.eb200_mul_add_batch(1, 4, None, z.ctypes.data, z.ctypes.data, z.ctypes.data, st.ctypes.data) == -3
     assert lib.eb200_strerror(-3).decode() == "invalid argument"
     # all-zero inputs are legal inputs: r = s = 0 -> FALSE for every item

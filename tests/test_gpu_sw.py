@@ -67,12 +67,13 @@ def test_fixed_base_table(native, name):
     tab = np.zeros(W * E * 2 * nl, np.uint32)
     nat.check(native.eb200_selftest_gtab(cid, tab.ctypes.data, tab.size))
     tab = tab.reshape(W, E, 2, nl)
-    R = 1 << (32 * nl)
+    # p256 / p384 / p521 hold plain residues (fp_special.cuh); p192 / p224 are in Montgomery form (fp_mont.cuh)
+    R = 1 if name in ("p256", "p384", "p521") else 1 << (32 * nl)
     rnd = random.Random(6)
     for j, i in [(0, 0), (0, E - 1), (W - 1, 0), (W - 1, E - 1)] + [(rnd.randrange(W), rnd.randrange(E)) for _ in range(30)]:
         pt = ec.g.mul(((2 * i + 1) << (B * j)) % n)
         x, y = ints(tab[j, i])
-        assert (x, y) == (pt.x * R % p, pt.y * R % p), (name, j, i)     # Montgomery form
+        assert (x, y) == (pt.x * R % p, pt.y * R % p), (name, j, i)
 
 
 @pytest.mark.parametrize("name", ["p256", "p384", "p521", "p192", "p224"])

@@ -539,3 +539,299 @@ def test_gq_group_law_matches_packed_field(he):
         assert to_aff(*run(1, jac, (p1.x, P - p1.y))) is None
         assert to_aff(*run(1, (1, 1, 0), (p2.x, p2.y))) == (p2.x, p2.y)
         assert to_aff(*run(0, (1, 1, 0), (p2.x, p2.y))) is None
+
+
+@pytest.mark.parametrize("cid,nl,p", [
+    (2, 8, 2**256 - 2**224 + 2**192 + 2**96 - 1), (3, 12, 2**384 - 2**128 - 2**96 + 2**32 - 1), (6, 18, 2**521 - 1),
+    (7, 6, 2**192 - 2**64 - 1), (8, 8, 2**224 - 2**96 + 1)])
+def test_sw_coordinate_field_ops(he, cid, nl, p):
+    """F::{mul, sqr, add, sub, neg, inv, toRed} of every short preset on values that stress the word-level
+    reductions of fp_special.cuh (all-ones / all-zero word patterns, p - small, values >= p)."""
+    rnd = random.Random(100 + cid)
+    bits = 32 * nl if cid != 6 else 528          # p521: what a 66-byte wire value can hold
+    top = 2**bits - 1
+    words = [0, 0xFFFFFFFF, 1, 0xFFFFFFFE, 0x80000000]
+    pats = [sum(rnd.choice(words) << (32 * i) for i in range(nl)) & top for _ in range(60)]
+    edge = [0, 1, 2, p - 1, p - 2, p, p + 1, top, top - 1, 2**(p.bit_length() - 1), (p + 1) // 2, 2**32, 2**96 - 1, 2**224, p - 2**96]
+    vals = [v & top for v in edge] + pats + [rnd.randrange(2**bits) for _ in range(60)]
+
+    def op(o, a, b=0):
+        out = (ctypes.c_uint32 * nl)()
+        he.he_sw_fe_op(cid, o, L(a, nl), L(b, nl), out)
+        return I(out, nl)
+    for a in vals:
+        for b in vals[:20] + pats[:8]:
+            assert op(0, a, b) == a * b % p, (hex(a), hex(b))
+            assert op(2, a, b) == (a + b) % p
+            assert op(3, a, b) == (a - b) % p
+        assert op(1, a) == a * a % p, hex(a)
+        assert op(4, a) == -a % p and op(6, a) == a % p
+    for a in vals[:10]:
+        assert op(7, a) == pow(a % p, p - 2, p)
+
+
+def test_eddsa_sign_body_reproduces_sign_input(he):
+    """EDDSA.sign (eddsa/index.js:34-44) through the kernel body: byte-identical signatures and public keys for the
+    reference's own test/fixtures/sign.input vectors (message lengths 0..1023)."""
+    import gzip
+    import json
+    data = json.load(gzip.open(os.path.join(ROOT, "tests", "golden", "ed25519_sign_input.json.gz"), "rt"))
+    vecs = data["vectors"][:40] + data["vectors"][-12:]
+    n = len(vecs)
+    sec = b"".join(bytes.fromhex(v["secret"]) for v in vecs)
+    msgs = [bytes.fromhex(v["msg"]) for v in vecs]
+    off = (ctypes.c_uint64 * (n + 1))(*np.concatenate([[0], np.cumsum([len(m) for m in msgs])]).astype(np.uint64))
+    sig, pub = (ctypes.c_uint8 * (64 * n))(), (ctypes.c_uint8 * (32 * n))()
+    he.he_ed25519_sign(ctypes.c_size_t(n), sec, b"".join(msgs) + b"\x00", off, sig, pub)
+    for i, v in enumerate(vecs):
+        assert bytes(sig[64 * i:64 * i + 64]).hex() == v["sig"], v["i"]
+        assert bytes(pub[32 * i:32 * i + 32]).hex() == v["pk"], v["i"]
+
+
+@pytest.mark.parametrize("name,cid,ln", [("secp256k1", 1, 32), ("p256", 2, 32), ("p384", 3, 48), ("p521", 6, 66), ("p192", 7, 24), ("p224", 8, 28)])
+def test_sign_options_and_keygen_bodies_against_oracle(he, name, cid, ln):
+    """EC.sign with options.k / options.pers (ec/index.js:143-157) and EC.genKeyPair({entropy, pers}) (:55-79)
+    through the kernel bodies, against the oracle."""
+    from oracle.ref_py.ec import EC
+    ec = EC(name)
+    n_ord = ec.n
+    rnd = random.Random(300 + cid)
+    W, E, B = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    he.he_gtab_dims(ctypes.byref(W), ctypes.byref(E), ctypes.byref(B))
+    gtab = np.zeros(W.value * E.value * 16, np.uint32)
+    if cid == 1:
+        he.he_gtab_fast(gtab.ctypes.data_as(ctypes.c_void_p))
+    cnt = 10 if ln < 66 else 5
+    privs = [rnd.randrange(1, n_ord) for _ in range(cnt)]
+    es = [rnd.randrange(min(n_ord, 1 << (8 * ln - 8))) for _ in range(cnt)]     # not shortened by _truncateToN (p521)
+    col = lambda vals: b"".join(v.to_bytes(ln, "big") for v in vals)
+    outs = lambda: ((ctypes.c_uint8 * (ln * cnt))(), (ctypes.c_uint8 * (ln * cnt))(), (ctypes.c_uint8 * cnt)(), (ctypes.c_uint8 * cnt)())
+    # ---- pers
+    for pers in (b"", b"my.pers", bytes(range(200))):
+        for canon in (0, 1):
+            r, s, rec, st = outs()
+            he.he_sign_opt(cid, 1, ctypes.c_size_t(cnt), col(es), col(privs), None, pers + b"\x00", len(pers), canon,
+                           gtab.ctypes.data_as(ctypes.c_void_p), r, s, rec, st)
+            for i in range(cnt):
+                sig = ec.sign(es[i], privs[i], canonical=bool(canon), pers=pers)
+                assert st[i] == 1
+                assert int.from_bytes(bytes(r[ln * i:ln * i + ln]), "big") == sig.r, (name, i)
+                assert int.from_bytes(bytes(s[ln * i:ln * i + ln]), "big") == sig.s and rec[i] == sig.recovery_param
+    # ---- caller nonces: a good k, then the loop's reject cases (k <= 1, k >= n - 1) which come back as RETRY (10)
+    ks = [rnd.randrange(2, n_ord - 1) for _ in range(cnt)]
+    ks[1], ks[2], ks[3] = 1, n_ord - 1, 0
+    if ln == 66:
+        ks[4] = (rnd.randrange(2, n_ord - 1) << 7) | 0x55           # 528-bit value: _truncateToN(k, true) shifts it by 7
+    r, s, rec, st = outs()
+    he.he_sign_opt(cid, 0, ctypes.c_size_t(cnt), col(es), col(privs), col(ks), None, 0, 0, gtab.ctypes.data_as(ctypes.c_void_p), r, s, rec, st)
+    for i in range(cnt):
+        calls = []
+
+        def kf(it, i=i, calls=calls):
+            calls.append(it)
+            return ks[i] if it == 0 else ec.n - 5 - i
+        sig = ec.sign(es[i], privs[i], k_fn=kf)
+        if len(calls) == 1:
+            assert st[i] == 1 and int.from_bytes(bytes(r[ln * i:ln * i + ln]), "big") == sig.r
+            assert int.from_bytes(bytes(s[ln * i:ln * i + ln]), "big") == sig.s and rec[i] == sig.recovery_param
+        else:
+            assert st[i] == 10, (name, i, st[i])
+    # (p521: n - 1 is a 521-bit value, so _truncateToN(k, true) shifts it by 7 and the reference accepts it)
+    assert st[1] == 10 and (st[2] == 10 or ln == 66) and st[3] == 10 and st[0] == 1
+    # ---- genKeyPair({entropy, pers})
+    for ne, pers in ((24, b""), (32, b""), (48, b"key-pers")):
+        ents = [bytes(rnd.randrange(256) for _ in range(ne)) for _ in range(cnt)]
+        out, st8 = (ctypes.c_uint8 * (ln * cnt))(), (ctypes.c_uint8 * cnt)()
+        he.he_keygen(cid, ctypes.c_size_t(cnt), b"".join(ents), ne, pers + b"\x00", len(pers), out, st8)
+        for i in range(cnt):
+            assert st8[i] == 1
+            assert int.from_bytes(bytes(out[ln * i:ln * i + ln]), "big") == ec.gen_key_pair(ents[i], pers).priv, (name, ne, i)
+
+
+def test_ec_api_over_ed25519_bodies_against_oracle(he):
+    """new elliptic.ec('ed25519') (test/ecdsa-test.js:130, test/ecdh-test.js:26): verify (eqXToP with up to eight
+    candidates), SEC1 keys incl. EdwardsCurve.pointFromX, sign (default / canonical / pers / k), genKeyPair, Point.mul /
+    mulAdd and KeyPair.derive through the kernel bodies, against the oracle."""
+    from oracle.ref_py.bn import RefError
+    from oracle.ref_py.ec import EC, KeyPair
+    ec = EC("ed25519")
+    n_ord, p = ec.n, ec.curve.p
+    rnd = random.Random(900)
+    cnt = 24
+    privs = [rnd.randrange(1, n_ord) for _ in range(cnt)]
+    pubs = [ec.g.mul(d) for d in privs]
+    es = [rnd.randrange(1 << 248) for _ in range(cnt)]
+    col = lambda vals: b"".join(v.to_bytes(32, "big") for v in vals)
+    # ---- sign: default, canonical, pers; then caller nonces
+    sigs = []
+    for pers in (b"", b"1234"):
+        for canon in (0, 1):
+            r, s = (ctypes.c_uint8 * (32 * cnt))(), (ctypes.c_uint8 * (32 * cnt))()
+            rec, st = (ctypes.c_uint8 * cnt)(), (ctypes.c_uint8 * cnt)()
+            he.he_ed_ec_sign(ctypes.c_size_t(cnt), col(es), col(privs), None, pers + b"\x00", len(pers), canon, r, s, rec, st)
+            for i in range(cnt):
+                sig = ec.sign(es[i], privs[i], canonical=bool(canon), pers=pers)
+                got = (int.from_bytes(bytes(r[32 * i:32 * i + 32]), "big"), int.from_bytes(bytes(s[32 * i:32 * i + 32]), "big"), rec[i])
+                assert st[i] == 1 and got == (sig.r, sig.s, sig.recovery_param), i
+                if not pers and not canon:
+                    sigs.append(sig)
+    ks = [rnd.randrange(2, n_ord - 1) for _ in range(cnt)]
+    ks[0], ks[1], ks[2], ks[3] = 1358, 1, n_ord - 1, (rnd.randrange(2, n_ord - 1) << 3) | 5      # 256-bit value: shifted by 3
+    r, s = (ctypes.c_uint8 * (32 * cnt))(), (ctypes.c_uint8 * (32 * cnt))()
+    rec, st = (ctypes.c_uint8 * cnt)(), (ctypes.c_uint8 * cnt)()
+    he.he_ed_ec_sign(ctypes.c_size_t(cnt), col(es), col(privs), col(ks), None, 0, 0, r, s, rec, st)
+    for i in range(cnt):
+        calls = []
+        sig = ec.sign(es[i], privs[i], k_fn=lambda it, i=i, calls=calls: (calls.append(it), ks[i] if it == 0 else 77 + i)[1])
+        if len(calls) == 1:
+            assert st[i] == 1 and int.from_bytes(bytes(r[32 * i:32 * i + 32]), "big") == sig.r and int.from_bytes(bytes(s[32 * i:32 * i + 32]), "big") == sig.s
+        else:
+            assert st[i] == 10
+    assert st[1] == 10 and st[0] == 1          # (n - 1 is a 32-byte value: _truncateToN(k, true) shifts it by 3 and the loop accepts it)
+    # ---- verify: valid, wrong key, flipped bits, range failures, off-curve key, SEC1 forms
+    items = []
+    for i in range(cnt):
+        e, rr, ss, q = es[i], sigs[i].r, sigs[i].s, pubs[i]
+        k = i % 8
+        if k == 1: e ^= 1 << rnd.randrange(240)
+        if k == 2: rr ^= 1 << rnd.randrange(250)
+        if k == 3: ss = n_ord - ss
+        if k == 4: q = pubs[(i + 1) % cnt]
+        if k == 5: rr = 0
+        if k == 6: ss = n_ord
+        items.append((e, rr, ss, q.get_x(), q.get_y()))
+    items.append((es[0], sigs[0].r, sigs[0].s, pubs[0].get_x(), (pubs[0].get_y() + 1) % p))       # off the curve
+    m = len(items)
+    stv = (ctypes.c_uint8 * m)()
+    he.he_ed_ec_verify(ctypes.c_size_t(m), col([t[0] for t in items]), col([t[1] for t in items]), col([t[2] for t in items]),
+                       b"".join(t[3].to_bytes(32, "big") + t[4].to_bytes(32, "big") for t in items), 0, stv)
+    for j, (e, rr, ss, x, y) in enumerate(items[:-1]):
+        want = int(ec.verify(e, {"r": rr, "s": ss}, {"x": x, "y": y})) if 1 <= rr < n_ord and 1 <= ss < n_ord else 0
+        assert stv[j] == want, j
+    assert stv[m - 1] == 4 and 1 in list(stv) and 0 in list(stv)
+    assert sum(1 for sg in sigs if sg.recovery_param & 2) > cnt // 2       # x(R) >= n: the multi-candidate loop is live
+    # compressed / uncompressed / hybrid keys through decodePoint + pointFromX
+    for fmt, size in ((2, 33), (1, 65)):
+        keys, exp = [], []
+        for i in range(cnt):
+            x, y = pubs[i].get_x(), pubs[i].get_y()
+            if fmt == 2:
+                tag = 3 if y & 1 else 2
+                if i % 6 == 5: tag ^= 1                                     # other root: a different (valid) point
+                if i % 6 == 4: tag = 5
+                kb = bytes([tag]) + (x if i % 6 != 3 else (x + 1) % p).to_bytes(32, "big")
+            else:
+                tag = [4, 6 if y % 2 == 0 else 7, 7 if y % 2 == 0 else 6, 9][i % 4]
+                kb = bytes([tag]) + x.to_bytes(32, "big") + y.to_bytes(32, "big")
+            keys.append(kb)
+            try:
+                exp.append(int(ec.verify(es[i], sigs[i], kb)))
+            except RefError as ex:
+                exp.append({"invalid point": 2, "Assertion failed": 5, "Unknown point format": 6}[ex.args[0]])
+        stv = (ctypes.c_uint8 * cnt)()
+        he.he_ed_ec_verify(ctypes.c_size_t(cnt), col(es), col([sg.r for sg in sigs]), col([sg.s for sg in sigs]), b"".join(keys), fmt, stv)
+        assert list(stv) == exp, (fmt, list(stv), exp)
+    # ---- genKeyPair
+    ents = [bytes(rnd.randrange(256) for _ in range(25)) for _ in range(cnt)]
+    out, st8 = (ctypes.c_uint8 * (32 * cnt))(), (ctypes.c_uint8 * cnt)()
+    he.he_ed_ec_keygen(ctypes.c_size_t(cnt), b"".join(ents), 25, b"\x00", 0, out, st8)
+    assert [int.from_bytes(bytes(out[32 * i:32 * i + 32]), "big") for i in range(cnt)] == [ec.gen_key_pair(x).priv for x in ents]
+    assert ec.gen_key_pair(bytes(range(1, 26))).priv == 0x5f305137244598fbe2e7bfe14ff6c3537fa37c392973908fc7820e2b24d4ea1
+    # ---- Point.mul / mulAdd / G.mul, KeyPair.derive
+    k1 = [rnd.randrange(2**256) for _ in range(cnt)]
+    k2 = [rnd.randrange(2**256) for _ in range(cnt)]
+    k2[0], k2[1], k1[2] = 0, n_ord, 0
+    pts = b"".join(q.get_x().to_bytes(32, "big") + q.get_y().to_bytes(32, "big") for q in pubs)
+    out, st8 = (ctypes.c_uint8 * (64 * cnt))(), (ctypes.c_uint8 * cnt)()
+    xy = lambda i: (int.from_bytes(bytes(out[64 * i:64 * i + 32]), "big"), int.from_bytes(bytes(out[64 * i + 32:64 * i + 64]), "big"))
+    he.he_ed_ec_mul_add(ctypes.c_size_t(cnt), col(k1), col(k2), pts, 0, out, st8)
+    for i in range(cnt):
+        w = ec.g.mul_add(k1[i] % n_ord, pubs[i], k2[i] % n_ord)
+        assert st8[i] == 1 and xy(i) == (w.get_x(), w.get_y()), i
+    he.he_ed_ec_mul_add(ctypes.c_size_t(cnt), None, col(k2), pts, 0, out, st8)
+    for i in range(cnt):
+        w = pubs[i].mul(k2[i] % n_ord)
+        assert xy(i) == (w.get_x(), w.get_y()), i
+    he.he_ed_ec_mul_add(ctypes.c_size_t(cnt), None, col(k2), None, 0, out, st8)
+    for i in range(cnt):
+        w = ec.g.mul(k2[i] % n_ord)
+        assert xy(i) == (w.get_x(), w.get_y()), i
+    he.he_ed_ec_mul_add(ctypes.c_size_t(cnt), None, col(privs), pts[64:] + pts[:64], 1, out, st8)
+    for i in range(cnt):
+        assert st8[i] == 1 and xy(i)[0] == KeyPair(ec, priv=privs[i]).derive(pubs[(i + 1) % cnt]), i
+    bad = bytearray(pts); bad[63] ^= 1
+    he.he_ed_ec_mul_add(ctypes.c_size_t(1), None, col(privs[:1]), bytes(bad[:64]), 1, out, st8)
+    assert st8[0] == 3
+    # ---- Montgomery-curve Point.mul (x only, no validation)
+    from oracle.ref_py import curves
+    c25 = curves.get("curve25519").curve
+    xs = [9, 9, 5] + [rnd.randrange(2**255 - 19) for _ in range(9)]
+    kk = [6, 0, 1] + [rnd.randrange(2**256) for _ in range(9)]
+    o2, s2 = (ctypes.c_uint8 * (32 * 12))(), (ctypes.c_uint8 * 12)()
+    he.he_x25519_mul(ctypes.c_size_t(12), col(kk), col(xs), o2, s2)
+    for i in range(12):
+        assert int.from_bytes(bytes(o2[32 * i:32 * i + 32]), "big") == c25.point(xs[i], 1).mul(kk[i]).get_x(), i
+
+
+def test_runtime_short_curve_bodies(he):
+    """sw_runtime.cuh (run-time p, a, b): add / dbl / mul / mulAdd / validate on the reference's toy curve
+    (test/curve-test.js:9-22: p = 0x1d, a = 4, b = 0x14) exhaustively, and on random prime fields, against
+    plain affine arithmetic."""
+    def params(p, a, b):
+        R = 1 << 256
+        return (L(p), L(R % p), L(R * R % p), L(a * R % p), L(b * R % p), (-pow(p, -1, 1 << 32)) % (1 << 32))
+
+    def aff_add(P, Q, p, a):
+        if P is None: return Q
+        if Q is None: return P
+        if P[0] == Q[0] and (P[1] + Q[1]) % p == 0: return None
+        lam = ((3 * P[0] * P[0] + a) * pow(2 * P[1], -1, p) if P == Q else (Q[1] - P[1]) * pow(Q[0] - P[0], -1, p)) % p
+        x = (lam * lam - P[0] - Q[0]) % p
+        return x, (lam * (P[0] - x) - P[1]) % p
+
+    def aff_mul(k, P, p, a):
+        R = None
+        for bit in bin(k)[2:] if k else "":
+            R = aff_add(R, R, p, a)
+            if bit == "1": R = aff_add(R, P, p, a)
+        return R
+
+    def run(prm, ln, op, P1, k1=0, P2=None, k2=None, klen=1):
+        pw, r1, r2, am, bm, n0 = prm
+        enc = lambda P: P[0].to_bytes(ln, "big") + P[1].to_bytes(ln, "big")
+        out, st = (ctypes.c_uint8 * (2 * ln))(), (ctypes.c_uint8 * 1)()
+        he.he_rt_item(op, pw, r1, r2, am, bm, ctypes.c_uint32(n0), ctypes.c_uint32(ln), k1.to_bytes(klen, "big"), enc(P1),
+                      k2.to_bytes(klen, "big") if k2 is not None else None, enc(P2) if P2 else None, ctypes.c_uint32(klen), out, st)
+        if st[0] == 1:
+            return int.from_bytes(bytes(out[:ln]), "big"), int.from_bytes(bytes(out[ln:]), "big")
+        return {7: None, 4: "off", 0: False}[st[0]]
+
+    p, a, b = 0x1d, 4, 0x14
+    prm = params(p, a, b)
+    pts = [(x, y) for x in range(p) for y in range(p) if (y * y - x ** 3 - a * x - b) % p == 0]
+    assert (0x18, 0x16) in pts                                             # the point the reference's test uses
+    for P in pts:
+        assert run(prm, 1, 2, P) == aff_add(P, P, p, a)
+        for Q in pts:
+            assert run(prm, 1, 1, P, P2=Q) == aff_add(P, Q, p, a)
+        for k in (0, 1, 2, 5, 36, 37, 255):
+            assert run(prm, 1, 0, P, k) == aff_mul(k, P, p, a)
+    assert run(prm, 1, 0, pts[3], 9, pts[7], 200) == aff_add(aff_mul(9, pts[3], p, a), aff_mul(200, pts[7], p, a), p, a)
+    assert run(prm, 1, 3, (3, 3)) is False and run(prm, 1, 0, (3, 3), 5) == "off"
+    rnd = random.Random(12)
+    for pp in (2**61 - 1, 2**127 - 1, 2**256 - 2**32 - 977, 2**256 - 2**224 + 2**192 + 2**96 - 1):      # all = 3 mod 4
+        ln = (pp.bit_length() + 7) // 8
+        aa, bb = rnd.randrange(pp), rnd.randrange(pp)
+        prm = params(pp, aa, bb)
+        found = []
+        while len(found) < 3:
+            x = rnd.randrange(pp)
+            rhs = (x ** 3 + aa * x + bb) % pp
+            if pow(rhs, (pp - 1) // 2, pp) == 1:
+                found.append((x, pow(rhs, (pp + 1) // 4, pp)))
+        P, Q, S = found
+        k1, k2 = rnd.randrange(2**200), rnd.randrange(2**64)
+        assert run(prm, ln, 1, P, P2=Q) == aff_add(P, Q, pp, aa)
+        assert run(prm, ln, 2, S) == aff_add(S, S, pp, aa)
+        assert run(prm, ln, 0, P, k1, klen=25) == aff_mul(k1, P, pp, aa)
+        assert run(prm, ln, 0, P, k1, Q, k2, klen=25) == aff_add(aff_mul(k1, P, pp, aa), aff_mul(k2, Q, pp, aa), pp, aa)

@@ -103,14 +103,10 @@ def test_ed25519_point_from_y_kat():
     assert "%x" % p.get_x() == v["x"]
 
 
-def test_ed25519_sign_input_vectors():
-    """test/ed25519-test.js:44-85 on the committed subset of test/fixtures/sign.input:
-    public key, exact signature, verify true, forged message false; cross-check with libsodium."""
+def _sign_input_chunk(vecs):
     import nacl.signing
-    import nacl.exceptions
-    data = json.load(gzip.open(os.path.join(G, "ed25519_sign_input.json.gz"), "rt"))
     ed = EDDSA()
-    for v in data["vectors"]:
+    for v in vecs:
         msg = bytes.fromhex(v["msg"])
         priv, _ = ed.priv_from_secret(v["secret"])
         assert ed.encode_point(ed.g.mul(priv)).hex() == v["pk"]
@@ -120,6 +116,20 @@ def test_ed25519_sign_input_vectors():
         forged[-1] = (forged[-1] + 1) & 0xFF
         assert ed.verify(bytes(forged), v["sig"], v["pk"]) is False
         nacl.signing.VerifyKey(bytes.fromhex(v["pk"])).verify(msg, bytes.fromhex(v["sig"]))
+    return len(vecs)
+
+
+def test_ed25519_sign_input_vectors():
+    """test/ed25519-test.js:44-85 on all 1024 lines of test/fixtures/sign.input: public key, exact signature,
+    verify true, forged message false; cross-check with libsodium.  (Worker processes: ~0.1 s per vector.)"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import benchdata
+    data = json.load(gzip.open(os.path.join(G, "ed25519_sign_input.json.gz"), "rt"))
+    vecs = data["vectors"]
+    assert len(vecs) == 1024
+    done = benchdata._pmap(_sign_input_chunk, [vecs[i:i + 16] for i in range(0, len(vecs), 16)], min_items=2)
+    assert sum(done) == 1024
 
 
 def test_ed25519_derivation_fixtures():
