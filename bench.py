@@ -335,9 +335,11 @@ def run_extra(key, log2n, mac32, alg_bytes, seed, lib, nat, dev, steps, imad_pea
         ec = EC("curve25519", device=dev.index)
         h = {k: torch.from_numpy(ds[k]).pin_memory().numpy() for k in ("priv", "pubx")}
         out_host = {}
+        h_out = torch.empty((n, 32), dtype=torch.uint8).pin_memory().numpy()         # the caller owns (and reuses) the result buffers
+        h_st = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
 
         def e2e_call():
-            out_host["x"], st = ec.derive_batch_packed(h["priv"], h["pubx"])
+            out_host["x"], st = ec.derive_batch_packed(h["priv"], h["pubx"], out=h_out, status=h_st)
             return st
         h2d, d2h = n * 64, n * 33
         api = "EC('curve25519').derive_batch_packed -> eb200_x25519_derive_batch"

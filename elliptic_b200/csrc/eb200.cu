@@ -1193,6 +1193,68 @@ static int finish_timing(Ctx& c, unsigned launches, bool main_is_total) {
   return EB200_OK;
 }
 
+// Generic two-stream chunk pipeline for the fixed-stride calls: chunk k's inputs go up on the copy stream, its
+// kernels run on stream (k & 1) (so the grid tail of one chunk is filled by the next), its outputs come home on the
+// copy stream behind them.  in(lo, m, seg) / out(lo, m, seg) fill up to 8 segments (out: dst = host, src = device);
+// run(lo, m, stream, slot, k) launches the kernels and records ev_k0[k] / ev_k1[k] around the main one.
+static void plan_chunks(size_t n, int* chunks, size_t* per) {
+  int ch = 1;
+  if (n >= ((size_t)1 << 18)) ch = 4;
+  if (n >= ((size_t)1 << 22)) ch = MAX_CHUNKS;
+  if (const char* ev = getenv("EB200_CHUNKS")) { int k = atoi(ev); if (k >= 1 && k <= MAX_CHUNKS) ch = k; }
+  size_t p = (n + ch - 1) / ch;
+  *chunks = ch;
+  *per = (p + 127) & ~(size_t)127;
+}
+
+template <class In, class Run, class Out>
+static int run_chunked(Ctx& c, size_t n, int chunks, size_t per, unsigned launches_per_chunk, In&& in, Run&& run, Out&& out) {
+  int rc;
+  cudaStream_t cs = c.copy_stream;
+  CK(cudaEventRecord(c.ev[0], cs));
+  int used = 0;
+  for (int k = 0; k < chunks; k++) {
+    size_t lo = (size_t)k * per;
+    if (lo >= n) break;
+    size_t m = (lo + per <= n) ? per : n - lo;
+    used = k + 1;
+    Seg seg[8];
+    int cnt = in(lo, m, seg);
+    if ((rc = h2d(c, seg, cnt, cs))) return rc;
+    CK(cudaEventRecord(c.ev_in[k], cs));
+    cudaStream_t ks = (k & 1) ? c.stream2 : c.stream;
+    CK(cudaStreamWaitEvent(ks, c.ev_in[k], 0));
+    if ((rc = run(lo, m, ks, k & 1, k))) return rc;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c.ev_done[k], ks));
+  }
+  for (int k = 0; k < used; k++) {
+    size_t lo = (size_t)k * per;
+    size_t m = (lo + per <= n) ? per : n - lo;
+    CK(cudaStreamWaitEvent(cs, c.ev_done[k], 0));
+    Seg seg[8];
+    int cnt = out(lo, m, seg);
+    for (int j = 0; j < cnt; j++)
+      if (seg[j].dst && seg[j].bytes) CK(cudaMemcpyAsync(seg[j].dst, seg[j].src, seg[j].bytes, cudaMemcpyDeviceToHost, cs));
+  }
+  CK(cudaEventRecord(c.ev[3], cs));
+  CK(cudaStreamSynchronize(cs));
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaStreamSynchronize(c.stream2));
+  float total = 0, t = 0;
+  cudaEventElapsedTime(&total, c.ev[0], c.ev[3]);
+  cudaEventElapsedTime(&c.timing.h2d_ms, c.ev[0], c.ev_in[used - 1]);
+  for (int k = 0; k < used; k++) {
+    cudaEventElapsedTime(&t, c.ev_k0[0], c.ev_k1[k]);
+    if (t > c.timing.main_kernel_ms) c.timing.main_kernel_ms = t;
+  }
+  cudaEventElapsedTime(&t, c.ev_done[used - 1], c.ev[3]);
+  c.timing.d2h_ms = t;
+  c.timing.kernel_ms = total;
+  c.timing.launches = launches_per_chunk * (unsigned)used;
+  return EB200_OK;
+}
+
 // DER-encoded signatures, parsed on the GPU (variable length: concatenated bytes + offsets; sig_off points at
 // this block's first offset, all offsets are absolute into `sigs`)
 static int verify_der_on(Ctx& c, int curve, size_t n, const uint8_t* e, const uint8_t* sigs, const uint64_t* sig_off,
@@ -1667,35 +1729,42 @@ static int eddsa_on(Ctx& c, size_t n, const uint8_t* R, const uint8_t* S, const 
                     const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status) {
   int rc = ensure_table(c, EB200_CURVE_ED25519);
   if (rc) return rc;
+  int chunks; size_t per;
+  plan_chunks(n, &chunks, &per);
   size_t mbytes = h ? 0 : (size_t)(msg_off[n] - msg_off[0]);
   size_t off_bytes = h ? 0 : (n + 1) * sizeof(uint64_t);
   size_t base = align256(n * 128);
+  const size_t ws_slot = eb200_eddsa_verify_workspace_bytes(per < n ? per : n);
   if ((rc = grow(&c.d_in, &c.d_in_cap, base + align256(off_bytes) + align256(mbytes + 1)))) return rc;
-  if ((rc = grow(&c.d_ws, &c.d_ws_cap, eb200_eddsa_verify_workspace_bytes(n)))) return rc;
+  if ((rc = grow(&c.d_ws, &c.d_ws_cap, (chunks > 1 ? 2 : 1) * ws_slot))) return rc;
   if ((rc = grow(&c.d_status, &c.d_status_cap, n))) return rc;
   uint8_t *dR = c.d_in, *dS = dR + 32 * n, *dA = dS + 32 * n, *dh = dA + 32 * n;
   uint64_t* doff = (uint64_t*)(c.d_in + base);
   uint8_t* dm = c.d_in + base + align256(off_bytes);
-  cudaStream_t st = c.stream;
-  unsigned nb = (unsigned)((n + 127) / 128), launches = 1;
-  CK(cudaEventRecord(c.ev[0], st));
-  Seg seg[5] = {{dR, R, 32 * n}, {dS, S, 32 * n}, {dA, A, 32 * n}, {h ? (void*)dh : (void*)doff, h ? (const void*)h : (const void*)msg_off, h ? 32 * n : off_bytes},
-                {dm, h ? nullptr : msgs + msg_off[0], mbytes}};
-  if ((rc = h2d(c, seg, 5, st))) return rc;
-  CK(cudaEventRecord(c.ev[1], st));
-  if (!h) {
-    ed25519_hash_kernel<<<nb, 128, 0, st>>>(n, dR, dA, dm - msg_off[0], doff, dh);
-    CK(cudaGetLastError());
-    launches = 2;
-  }
-  CK(cudaEventRecord(c.ev[4], st));
-  ed25519_verify_kernel<<<nb, 128, 0, st>>>(n, dR, dS, dA, dh, c.gtab[EB200_CURVE_ED25519], (u32*)c.d_ws, c.d_status);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(c.ev[5], st));
-  CK(cudaEventRecord(c.ev[2], st));
-  CK(cudaMemcpyAsync(status, c.d_status, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(c.ev[3], st));
-  return finish_timing(c, launches, false);
+  const u32* gt = c.gtab[EB200_CURVE_ED25519];
+  return run_chunked(c, n, chunks, per, h ? 1u : 2u,
+    [&](size_t lo, size_t m, Seg* seg) {
+      seg[0] = {dR + 32 * lo, R + 32 * lo, 32 * m};
+      seg[1] = {dS + 32 * lo, S + 32 * lo, 32 * m};
+      seg[2] = {dA + 32 * lo, A + 32 * lo, 32 * m};
+      if (h) { seg[3] = {dh + 32 * lo, h + 32 * lo, 32 * m}; return 4; }
+      seg[3] = {doff + lo, msg_off + lo, (m + 1) * sizeof(uint64_t)};
+      seg[4] = {dm + (msg_off[lo] - msg_off[0]), msgs + msg_off[lo], (size_t)(msg_off[lo + m] - msg_off[lo])};
+      return 5;
+    },
+    [&](size_t lo, size_t m, cudaStream_t ks, int slot, int k) {
+      unsigned nb = (unsigned)((m + 127) / 128);
+      if (!h) ed25519_hash_kernel<<<nb, 128, 0, ks>>>(m, dR + 32 * lo, dA + 32 * lo, dm - msg_off[0], doff + lo, dh + 32 * lo);
+      CK(cudaEventRecord(c.ev_k0[k], ks));
+      ed25519_verify_kernel<<<nb, 128, 0, ks>>>(m, dR + 32 * lo, dS + 32 * lo, dA + 32 * lo, dh + 32 * lo, gt,
+                                                (u32*)(c.d_ws + (size_t)slot * ws_slot), c.d_status + lo);
+      CK(cudaEventRecord(c.ev_k1[k], ks));
+      return EB200_OK;
+    },
+    [&](size_t lo, size_t m, Seg* seg) {
+      seg[0] = {status + lo, c.d_status + lo, m};
+      return 1;
+    });
 }
 
 // EDDSA.sign batch: secrets n x 32, raw messages (offsets absolute, msg_off points at this block's first one)
@@ -1729,23 +1798,31 @@ static int eddsa_sign_on(Ctx& c, size_t n, const uint8_t* secrets, const uint8_t
 
 static int x25519_on(Ctx& c, size_t n, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status, bool validate) {
   int rc;
+  int chunks; size_t per;
+  plan_chunks(n, &chunks, &per);
   if ((rc = grow(&c.d_in, &c.d_in_cap, n * 96))) return rc;
   if ((rc = grow(&c.d_status, &c.d_status_cap, n))) return rc;
   uint8_t *dk = c.d_in, *dx = dk + 32 * n, *dout = dx + 32 * n;
-  cudaStream_t st = c.stream;
-  CK(cudaEventRecord(c.ev[0], st));
-  Seg seg[2] = {{dk, priv, 32 * n}, {dx, pubx, 32 * n}};
-  if ((rc = h2d(c, seg, 2, st))) return rc;
-  CK(cudaEventRecord(c.ev[1], st));
-  if (validate) x25519_derive_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dk, dx, dout, c.d_status);
-  else x25519_mul_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n, dk, dx, dout, c.d_status);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(c.ev[2], st));
-  CK(cudaMemcpyAsync(out, dout, 32 * n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(status, c.d_status, n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemsetAsync(dk, 0, 32 * n, st));               // private scalars do not stay in the shared buffer
-  CK(cudaEventRecord(c.ev[3], st));
-  return finish_timing(c, 1, true);
+  return run_chunked(c, n, chunks, per, 1u,
+    [&](size_t lo, size_t m, Seg* seg) {
+      seg[0] = {dk + 32 * lo, priv + 32 * lo, 32 * m};
+      seg[1] = {dx + 32 * lo, pubx + 32 * lo, 32 * m};
+      return 2;
+    },
+    [&](size_t lo, size_t m, cudaStream_t ks, int, int k) {
+      unsigned nb = (unsigned)((m + 127) / 128);
+      CK(cudaEventRecord(c.ev_k0[k], ks));
+      if (validate) x25519_derive_kernel<<<nb, 128, 0, ks>>>(m, dk + 32 * lo, dx + 32 * lo, dout + 32 * lo, c.d_status + lo);
+      else x25519_mul_kernel<<<nb, 128, 0, ks>>>(m, dk + 32 * lo, dx + 32 * lo, dout + 32 * lo, c.d_status + lo);
+      CK(cudaEventRecord(c.ev_k1[k], ks));
+      CK(cudaMemsetAsync(dk + 32 * lo, 0, 32 * m, ks));   // private scalars do not stay in the shared buffer
+      return EB200_OK;
+    },
+    [&](size_t lo, size_t m, Seg* seg) {
+      seg[0] = {out + 32 * lo, dout + 32 * lo, 32 * m};
+      seg[1] = {status + lo, c.d_status + lo, m};
+      return 2;
+    });
 }
 
 extern "C" {

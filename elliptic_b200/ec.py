@@ -546,9 +546,10 @@ class EC:
         vals = [int.from_bytes(out[i].tobytes(), "big") if st[i] == nat.ST_TRUE else None for i in range(n)]
         return vals, st
 
-    def derive_batch_packed(self, priv, pubx):
+    def derive_batch_packed(self, priv, pubx, out=None, status=None):
         """Packed curve25519 ECDH: priv, pubx are (n, 32) uint8 arrays (big-endian; priv already reduced mod n as
-        _importPrivate does, ec/key.js:76-82).  Returns ((n, 32) shared x big-endian, statuses)."""
+        _importPrivate does, ec/key.js:76-82).  Returns ((n, 32) shared x big-endian, statuses); `out` / `status`
+        let the caller supply (and reuse) the result buffers, e.g. pinned ones."""
         if self.name != "curve25519":
             raise EllipticError("derive_batch_packed: curve25519 only (short curves: derive_batch)")
         lib = nat.init(self._device)
@@ -557,8 +558,10 @@ class EC:
         n = priv.shape[0]
         if priv.shape != (n, 32) or pubx.shape != (n, 32):
             raise EllipticError("derive_batch_packed: (n, 32) arrays expected")
-        out = np.empty((n, 32), np.uint8)
-        st = np.empty(n, np.uint8)
+        out = np.empty((n, 32), np.uint8) if out is None else out
+        st = np.empty(n, np.uint8) if status is None else status
+        if out.shape != (n, 32) or out.dtype != np.uint8 or not out.flags.c_contiguous or st.shape != (n,) or st.dtype != np.uint8:
+            raise EllipticError("derive_batch_packed: out must be a contiguous (n, 32) uint8 array, status (n,) uint8")
         nat.check(lib.eb200_x25519_derive_batch(n, priv.ctypes.data, pubx.ctypes.data, out.ctypes.data, st.ctypes.data))
         return out, st
 
