@@ -205,7 +205,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "verifies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -562,7 +562,7 @@ def run_gpu(args):
                     wl[key] = run_extra(key, log2n, mac32, alg_bytes, seed, lib, nat, dev, max(3, min(args.steps, 5)), imad_peak)
                     torch.cuda.empty_cache()
                 line["workloads"] = wl
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -651,10 +651,31 @@ def run_single_process(args):
                 "api": "one EC.verify_batch_packed -> eb200_ecdsa_verify_batch call over %d x 2^20 items" % N},
         "gpu_launches": int(tm["launches"]) * 0 + 5 * N * args.steps, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to fd 1
+    whatever NCCL_DEBUG_FILE says; child processes inherit fd 1), so fd 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

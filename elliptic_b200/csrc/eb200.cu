@@ -546,6 +546,57 @@ constexpr int STAGE_SLOTS = 8;                       // pinned staging ring for 
 constexpr size_t STAGE_BYTES = (size_t)4 << 20;
 constexpr size_t SHARD_MIN_ITEMS = (size_t)1 << 14;  // below this per device a second GPU does not pay
 
+// ---- parallel host memcpy (pageable caller buffers -> pinned staging slots) ----------------------------
+struct CopyJob { void* dst; const void* src; size_t bytes; };
+class CopyPool {
+ public:
+  void run(const CopyJob* j, int n) {
+    if (n <= 0) return;
+    std::lock_guard<std::mutex> one(call_mu_);
+    if (n == 1) { memcpy(j[0].dst, j[0].src, j[0].bytes); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      if (workers_.empty()) for (int t = 0; t < 3; t++) workers_.emplace_back([this] { loop(); });
+      jobs_.store(j); njobs_.store(n); next_.store(0); pending_ = n; gen_++;
+    }
+    cv_work_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return pending_ == 0; });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_work_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+ private:
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      { std::unique_lock<std::mutex> lk(m_); cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; }
+      work();
+    }
+  }
+  void work() {
+    for (;;) {
+      int i = next_.fetch_add(1);
+      if (i >= njobs_.load()) break;
+      const CopyJob* j = jobs_.load();
+      memcpy(j[i].dst, j[i].src, j[i].bytes);
+      std::lock_guard<std::mutex> lk(m_);
+      if (--pending_ == 0) cv_done_.notify_all();
+    }
+  }
+  std::mutex m_, call_mu_;
+  std::condition_variable cv_work_, cv_done_;
+  std::vector<std::thread> workers_;
+  std::atomic<const CopyJob*> jobs_{nullptr};
+  std::atomic<int> njobs_{0}, next_{0};
+  int pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+
 struct Ctx {
   std::mutex mu;                      // serialises the calls that use this device's buffers / events
   bool ready = false;
@@ -563,6 +614,7 @@ struct Ctx {
   cudaEvent_t ev_stage[STAGE_SLOTS] = {};
   bool stage_used[STAGE_SLOTS] = {};
   unsigned stage_next = 0;
+  CopyPool pool;                                       // this device's staging copies (one pool per device: no cross-device serialisation)
   eb200_timing timing = {};
 };
 Ctx g_ctx[MAX_DEV];
@@ -630,57 +682,6 @@ WsLayout ws_layout(int curve, size_t n) {
   return L;
 }
 
-// ---- parallel host memcpy (pageable caller buffers -> pinned staging slots) ----------------------------
-struct CopyJob { void* dst; const void* src; size_t bytes; };
-class CopyPool {
- public:
-  void run(const CopyJob* j, int n) {
-    if (n <= 0) return;
-    std::lock_guard<std::mutex> one(call_mu_);
-    if (n == 1) { memcpy(j[0].dst, j[0].src, j[0].bytes); return; }
-    {
-      std::lock_guard<std::mutex> lk(m_);
-      if (workers_.empty()) for (int t = 0; t < 3; t++) workers_.emplace_back([this] { loop(); });
-      jobs_.store(j); njobs_.store(n); next_.store(0); pending_ = n; gen_++;
-    }
-    cv_work_.notify_all();
-    work();
-    std::unique_lock<std::mutex> lk(m_);
-    cv_done_.wait(lk, [&] { return pending_ == 0; });
-  }
-  ~CopyPool() {
-    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
-    cv_work_.notify_all();
-    for (auto& t : workers_) t.join();
-  }
- private:
-  void loop() {
-    unsigned long long seen = 0;
-    for (;;) {
-      { std::unique_lock<std::mutex> lk(m_); cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; }); if (stop_) return; seen = gen_; }
-      work();
-    }
-  }
-  void work() {
-    for (;;) {
-      int i = next_.fetch_add(1);
-      if (i >= njobs_.load()) break;
-      const CopyJob* j = jobs_.load();
-      memcpy(j[i].dst, j[i].src, j[i].bytes);
-      std::lock_guard<std::mutex> lk(m_);
-      if (--pending_ == 0) cv_done_.notify_all();
-    }
-  }
-  std::mutex m_, call_mu_;
-  std::condition_variable cv_work_, cv_done_;
-  std::vector<std::thread> workers_;
-  std::atomic<const CopyJob*> jobs_{nullptr};
-  std::atomic<int> njobs_{0}, next_{0};
-  int pending_ = 0;
-  unsigned long long gen_ = 0;
-  bool stop_ = false;
-};
-CopyPool g_pool;
 
 bool is_pinned(const void* p) {
   cudaPointerAttributes a;
@@ -721,7 +722,7 @@ int h2d(Ctx& c, const Seg* seg, int k, cudaStream_t st) {
       nj++;
       off += m;
       if (nj == 4) {
-        g_pool.run(jobs, nj);
+        c.pool.run(jobs, nj);
         for (int j = 0; j < nj; j++) {
           CK(cudaMemcpyAsync(dsts[j], jobs[j].dst, jobs[j].bytes, cudaMemcpyHostToDevice, st));
           CK(cudaEventRecord(c.ev_stage[slots[j]], st));
@@ -732,7 +733,7 @@ int h2d(Ctx& c, const Seg* seg, int k, cudaStream_t st) {
     }
   }
   if (nj) {
-    g_pool.run(jobs, nj);
+    c.pool.run(jobs, nj);
     for (int j = 0; j < nj; j++) {
       CK(cudaMemcpyAsync(dsts[j], jobs[j].dst, jobs[j].bytes, cudaMemcpyHostToDevice, st));
       CK(cudaEventRecord(c.ev_stage[slots[j]], st));

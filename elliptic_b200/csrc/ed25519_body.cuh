@@ -372,16 +372,12 @@ EB_HD uint8_t x25519_ladder_item(size_t i, const uint8_t* priv, const uint8_t* p
   load_be<8>(k, priv + 32 * i);
   f25 x;
   load_be<8>(x.v, pubx + 32 * i);                     // toRed reduces mod p; weak form is fine here
+  // validate (mont.js:21-28): rhs = x^3 + A x^2 + x must be a square (or 0).  The residue test is NOT done here:
+  // it shares one exponentiation with the inversion of the ladder's z at the end (f25_pow_p32).
+  f25 rhs = f25_zero();
   if (VALIDATE) {
-    // validate: x^3 + A x^2 + x must be a square (or 0)
     f25 x2 = f25_sqr(x);
-    f25 rhs = f25_add(f25_add(f25_mul(x2, x), f25_mul_small(x2, 486662u)), x);
-    f25 leg = f25_normalize(f25_legendre(rhs));
-    bool is_qr = is_zero_n<8>(leg.v) || (leg.v[0] == 1 && (leg.v[1] | leg.v[2] | leg.v[3] | leg.v[4] | leg.v[5] | leg.v[6] | leg.v[7]) == 0);
-    if (!is_qr) {
-      for (int b = 0; b < 32; b++) out[32 * i + b] = 0;
-      return 5;
-    }
+    rhs = f25_add(f25_add(f25_mul(x2, x), f25_mul_small(x2, 486662u)), x);
   }
   // Montgomery ladder, MSB first (mont.js:130-153): (a, b) = ((m+1)P, mP), diff = P = (x : 1)
   f25 ax = x, az = f25_one(), bx = f25_one(), bz = f25_zero();
@@ -407,7 +403,30 @@ EB_HD uint8_t x25519_ladder_item(size_t i, const uint8_t* priv, const uint8_t* p
     ax = f25_cmov(nx, dx, one); az = f25_cmov(nz, dz, one);
     bx = f25_cmov(dx, nx, one); bz = f25_cmov(dz, nz, one);
   }
-  f25 r = f25_normalize(f25_mul(bx, f25_inv(bz)));    // getX: x * z^-1, with inv(0) = 0 (mont.js:167-178)
+  f25 zinv;
+  if (VALIDATE) {
+    // y = rhs z^2 has the Legendre symbol of rhs; e = y^((p-3)/2): y e = chi(y), chi e = 1 / y, 1 / z = rhs z / y
+    f25 y = f25_mul(rhs, f25_sqr(bz));
+    f25 e = f25_pow_p32(y);
+    f25 chi = f25_normalize(f25_mul(y, e));
+    bool chi_one = chi.v[0] == 1 && (chi.v[1] | chi.v[2] | chi.v[3] | chi.v[4] | chi.v[5] | chi.v[6] | chi.v[7]) == 0;
+    bool is_qr = chi_one;
+    if (is_zero_n<8>(chi.v)) {
+      // rhs == 0 or z == 0 (low-order inputs): the two questions are answered separately, as the reference does
+      f25 leg = f25_normalize(f25_legendre(rhs));
+      is_qr = is_zero_n<8>(leg.v) || (leg.v[0] == 1 && (leg.v[1] | leg.v[2] | leg.v[3] | leg.v[4] | leg.v[5] | leg.v[6] | leg.v[7]) == 0);
+      zinv = f25_inv(bz);
+    } else {
+      zinv = f25_mul(f25_mul(e, rhs), bz);
+    }
+    if (!is_qr) {
+      for (int b = 0; b < 32; b++) out[32 * i + b] = 0;
+      return 5;
+    }
+  } else {
+    zinv = f25_inv(bz);
+  }
+  f25 r = f25_normalize(f25_mul(bx, zinv));           // getX: x * z^-1, with inv(0) = 0 (mont.js:167-178)
   store_be<8>(out + 32 * i, r.v);
   return 1;
 }

@@ -278,6 +278,15 @@ EB_HD f25 f25_legendre(const f25& a) {
   return f25_mul(f25_sqr_n(t, 4), a6);
 }
 
+// a^((p-3)/2) = a^(2^254 - 11) = (a^(2^250 - 1))^(2^4) * a^5.  For a != 0: a * this = chi(a) (Legendre symbol) and
+// chi(a) * this = 1 / a -- one exponentiation answers "is a a square" AND inverts it.
+EB_HD f25 f25_pow_p32(const f25& a) {
+  f25 a11;
+  f25 t = f25_pow_2_250_1(a, &a11);
+  f25 a5 = f25_mul(f25_sqr_n(a, 2), a);
+  return f25_mul(f25_sqr_n(t, 4), a5);
+}
+
 EB_HD f25 f25_sqrt_m1() {   // 2^((p-1)/4)
   f25 r;
   const u32 v[8] = {0x4a0ea0b0u, 0xc4ee1b27u, 0xad2fe478u, 0x2f431806u, 0x3dfbd7a7u, 0x2b4d0099u, 0x4fc1df0bu, 0x2b832480u};

@@ -11,6 +11,12 @@
 // the ALU pipe in the shadow of the fma pipe.
 #pragma once
 #include "limbs.cuh"
+#include "mul_cs.cuh"
+
+// EB_MUL_CS=1: wide products from carry-out-only MACs (mul_cs.cuh) instead of the mad.lo.cc / madc.hi.cc chains
+#ifndef EB_MUL_CS
+#define EB_MUL_CS 0
+#endif
 
 namespace eb {
 
@@ -127,7 +133,9 @@ EB_HD void fe_reduce512(u32* r, const u32* t) {
 #include "sqr_gen.inc"
 #endif
 EB_HD void fe_sqr_wide(u32* r, const u32* a) {
-#if defined(__CUDA_ARCH__) && !defined(EB_SQR_AS_MUL)
+#if defined(__CUDA_ARCH__) && EB_MUL_CS
+  sqr_wide_cs<8>(r, a);
+#elif defined(__CUDA_ARCH__) && !defined(EB_SQR_AS_MUL)
   sqr_wide8_ptx(r, a);
 #else
   mul_wide<8>(r, a, a);
@@ -136,7 +144,11 @@ EB_HD void fe_sqr_wide(u32* r, const u32* a) {
 
 EB_HD fe fe_mul_inl(const fe& a, const fe& b) {
   u32 t[16];
+#if defined(__CUDA_ARCH__) && EB_MUL_CS
+  mul_wide_cs<8>(t, a.v, b.v);
+#else
   mul_wide<8>(t, a.v, b.v);
+#endif
   fe r;
   fe_reduce512(r.v, t);
   return r;
@@ -174,6 +186,18 @@ EB_HD fe fe_sqr_hot(const fe& a) { return fe_sqr(a); }
 EB_HD fe fe_mul(const fe& a, const fe& b) { return fe_mul_inl(a, b); }
 EB_HD fe fe_sqr(const fe& a) { return fe_sqr_inl(a); }
 EB_HD fe fe_sqr_hot(const fe& a) { return fe_sqr_inl(a); }
+#endif
+
+// Two independent products per call (EB_FE_MUL2=1): half the calls of the group-law bodies, and two carry chains
+// for the scheduler to interleave inside one body.
+#ifndef EB_FE_MUL2
+#define EB_FE_MUL2 0
+#endif
+struct fe2 { fe a, b; };
+#if defined(__CUDACC__) && EB_FE_OUTLINE
+__host__ __device__ __noinline__ fe2 fe_mul2(fe a, fe b, fe c, fe d) { fe2 r; r.a = fe_mul_inl(a, b); r.b = fe_mul_inl(c, d); return r; }
+#else
+EB_HD fe2 fe_mul2(const fe& a, const fe& b, const fe& c, const fe& d) { fe2 r; r.a = fe_mul_inl(a, b); r.b = fe_mul_inl(c, d); return r; }
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -48,8 +48,14 @@ EB_HD ge_jac jac_dbl_inl(const ge_jac& p) {
   ge_jac r;
   r.x = fe_sub(F, fe_dbl(D));
   fe C8 = fe_mul_small(C, 8);
+#if EB_FE_MUL2
+  fe2 m = fe_mul2(E, fe_sub(D, r.x), p.y, p.z);
+  r.y = fe_sub(m.a, C8);
+  r.z = fe_dbl(m.b);
+#else
   r.y = fe_sub(fe_mul(E, fe_sub(D, r.x)), C8);
   r.z = fe_dbl(fe_mul(p.y, p.z));
+#endif
   return r;
 }
 
@@ -60,6 +66,20 @@ EB_HD ge_jac jac_dbl_aff(const ge_aff& p) { return jac_dbl_inl(jac_from_aff(p));
 // (short.js:569-603.)
 EB_HD ge_jac jac_madd_inl(const ge_jac& a, const ge_aff& p) {
   fe z2 = fe_sqr_hot(a.z);
+#if EB_FE_MUL2
+  fe2 m1 = fe_mul2(p.x, z2, p.y, z2);            // u2, y2 z1^2
+  fe h = fe_sub(a.x, m1.a);
+  fe2 m2 = fe_mul2(m1.b, a.z, a.z, h);           // s2, z3
+  fe rr = fe_sub(a.y, m2.a);
+  fe h2 = fe_sqr_hot(h);
+  fe2 m3 = fe_mul2(h2, h, a.x, h2);              // h^3, v
+  fe h3 = m3.a, v = m3.b;
+  ge_jac r;
+  r.x = fe_sub(fe_sub(fe_add(fe_sqr_hot(rr), h3), v), v);
+  fe2 m4 = fe_mul2(rr, fe_sub(v, r.x), a.y, h3);
+  r.y = fe_sub(m4.a, m4.b);
+  r.z = m2.b;
+#else
   fe u2 = fe_mul(p.x, z2);
   fe s2 = fe_mul(fe_mul(p.y, z2), a.z);
   fe h = fe_sub(a.x, u2);
@@ -71,6 +91,7 @@ EB_HD ge_jac jac_madd_inl(const ge_jac& a, const ge_aff& p) {
   r.x = fe_sub(fe_sub(fe_add(fe_sqr_hot(rr), h3), v), v);
   r.y = fe_sub(fe_mul(rr, fe_sub(v, r.x)), fe_mul(a.y, h3));
   r.z = fe_mul(a.z, h);
+#endif
   if (fe_is_zero(r.z)) {                       // cold: a == inf, or h == 0
     if (fe_is_zero(a.z)) return jac_from_aff(p);   // O + P = P      (short.js:571-572)
     if (fe_is_zero(rr)) return jac_dbl_inl(a);     // P + P = 2P     (short.js:591)
