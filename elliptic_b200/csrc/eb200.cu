@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(128) sw_prep_kernel(size_t N, const uint8_t* _
   SW<C>::prep_thread(tid, T, N, e, r, s, ws, scratch);
 }
 #ifndef EB_SW_MINBLOCKS8
-#define EB_SW_MINBLOCKS8 3        // 8-limb curves (p256, p224): three 128-thread blocks per SM (168 registers)
-#endif
+#define EB_SW_MINBLOCKS8 4        // 8-limb curves (p256, p224): four 128-thread blocks per SM (128 registers, 224 B of
+#endif                            // spill): 51.1 ms against 52.2 ms with three blocks / 168 registers at N = 2^20 (r02)
 template <class C>
 __global__ void __launch_bounds__(128, (C::N <= 8) ? EB_SW_MINBLOCKS8 : 2)
 sw_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __restrict__ r, const u32* __restrict__ ws,
@@ -1117,17 +1117,50 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
 
 // Host-pointer verify on one device.  Large batches are cut into chunks: chunk k+1 is copied host->device on a
 // copy stream while chunk k is being verified, and results stream back as each chunk finishes.
+// Chunk boundaries of a pipelined host call.  Equal chunks, except that the FIRST one is cut short (1/4 of a
+// regular chunk): its host->device copy is the only one no kernel hides, so the shorter it is the sooner the GPU
+// starts (EB200_LEAD=0 restores equal chunks; EB200_CHUNKS overrides the count).
+struct ChunkPlan { int chunks; size_t lo[MAX_CHUNKS + 2]; size_t max_m; };
+static ChunkPlan make_plan(size_t n) {
+  int ch = 1;
+  if (n >= ((size_t)1 << 18)) ch = 4;         // 2^18-item chunks keep the grid tail small (r01: 8 chunks cost 10%)
+  if (n >= ((size_t)1 << 22)) ch = MAX_CHUNKS;
+  if (const char* ev = getenv("EB200_CHUNKS")) { int k = atoi(ev); if (k >= 1 && k <= MAX_CHUNKS) ch = k; }   // tuning knob
+  bool lead = ch > 1 && ch < MAX_CHUNKS;
+  if (const char* ev = getenv("EB200_LEAD")) lead = lead && atoi(ev) != 0;
+  ChunkPlan P;
+  size_t per = (n + ch - 1) / ch;
+  per = (per + 127) & ~(size_t)127;
+  int k = 0;
+  size_t pos = 0;
+  P.lo[0] = 0;
+  if (lead) {
+    size_t first = ((per / 4) + 127) & ~(size_t)127;
+    if (first < n) {
+      pos = first;
+      P.lo[++k] = pos;
+      per = (n - first + ch - 1) / ch;
+      per = (per + 127) & ~(size_t)127;
+    }
+  }
+  while (pos < n) {
+    pos = pos + per < n ? pos + per : n;
+    P.lo[++k] = pos;
+  }
+  P.chunks = k;
+  P.max_m = 0;
+  for (int i = 0; i < k; i++) if (P.lo[i + 1] - P.lo[i] > P.max_m) P.max_m = P.lo[i + 1] - P.lo[i];
+  return P;
+}
+
 static int verify_on(Ctx& c, int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
                      uint32_t pub_fmt, uint8_t* status) {
   int rc = ensure_table(c, curve);
   if (rc) return rc;
   const size_t len = curve_len(curve), pb = pub_item_bytes(len, pub_fmt);
-  int chunks = 1;
-  if (n >= ((size_t)1 << 18)) chunks = 4;     // 2^18-item chunks keep the grid tail small (r01: 8 chunks cost 10%)
-  if (n >= ((size_t)1 << 22)) chunks = MAX_CHUNKS;
-  if (const char* ev = getenv("EB200_CHUNKS")) { int k = atoi(ev); if (k >= 1 && k <= MAX_CHUNKS) chunks = k; }   // tuning knob
-  size_t per = (n + chunks - 1) / chunks;
-  per = (per + 127) & ~(size_t)127;
+  const ChunkPlan P = make_plan(n);
+  const int chunks = P.chunks;
+  const size_t per = P.max_m;
   size_t item_in = 3 * len + pb;
   if ((rc = grow(&c.d_in, &c.d_in_cap, align256(n * item_in) + 1024))) return rc;
   // two chunks in flight (alternating compute streams, so the grid tail of chunk k is filled by chunk k+1)
@@ -1143,9 +1176,8 @@ static int verify_on(Ctx& c, int curve, size_t n, const uint8_t* e, const uint8_
   CK(cudaEventRecord(c.ev[0], cs));
   int used = 0;
   for (int k = 0; k < chunks; k++) {
-    size_t lo = (size_t)k * per;
-    if (lo >= n) break;
-    size_t m = (lo + per <= n) ? per : n - lo;
+    size_t lo = P.lo[k];
+    size_t m = P.lo[k + 1] - lo;
     used = k + 1;
     Seg seg[4] = {{d_e + lo * len, e + lo * len, m * len}, {d_r + lo * len, r + lo * len, m * len},
                   {d_s + lo * len, s + lo * len, m * len}, {d_pub + lo * pb, pub + lo * pb, m * pb}};
@@ -1159,8 +1191,8 @@ static int verify_on(Ctx& c, int curve, size_t n, const uint8_t* e, const uint8_
   }
   // results: one device->host copy per chunk, behind that chunk's kernels, on the copy stream
   for (int k = 0; k < used; k++) {
-    size_t lo = (size_t)k * per;
-    size_t m = (lo + per <= n) ? per : n - lo;
+    size_t lo = P.lo[k];
+    size_t m = P.lo[k + 1] - lo;
     CK(cudaStreamWaitEvent(cs, c.ev_done[k], 0));
     CK(cudaMemcpyAsync(status + lo, c.d_status + lo, m, cudaMemcpyDeviceToHost, cs));
   }
@@ -1198,26 +1230,15 @@ static int finish_timing(Ctx& c, unsigned launches, bool main_is_total) {
 // kernels run on stream (k & 1) (so the grid tail of one chunk is filled by the next), its outputs come home on the
 // copy stream behind them.  in(lo, m, seg) / out(lo, m, seg) fill up to 8 segments (out: dst = host, src = device);
 // run(lo, m, stream, slot, k) launches the kernels and records ev_k0[k] / ev_k1[k] around the main one.
-static void plan_chunks(size_t n, int* chunks, size_t* per) {
-  int ch = 1;
-  if (n >= ((size_t)1 << 18)) ch = 4;
-  if (n >= ((size_t)1 << 22)) ch = MAX_CHUNKS;
-  if (const char* ev = getenv("EB200_CHUNKS")) { int k = atoi(ev); if (k >= 1 && k <= MAX_CHUNKS) ch = k; }
-  size_t p = (n + ch - 1) / ch;
-  *chunks = ch;
-  *per = (p + 127) & ~(size_t)127;
-}
-
 template <class In, class Run, class Out>
-static int run_chunked(Ctx& c, size_t n, int chunks, size_t per, unsigned launches_per_chunk, In&& in, Run&& run, Out&& out) {
+static int run_chunked(Ctx& c, const ChunkPlan& P, unsigned launches_per_chunk, In&& in, Run&& run, Out&& out) {
   int rc;
   cudaStream_t cs = c.copy_stream;
   CK(cudaEventRecord(c.ev[0], cs));
   int used = 0;
-  for (int k = 0; k < chunks; k++) {
-    size_t lo = (size_t)k * per;
-    if (lo >= n) break;
-    size_t m = (lo + per <= n) ? per : n - lo;
+  for (int k = 0; k < P.chunks; k++) {
+    size_t lo = P.lo[k];
+    size_t m = P.lo[k + 1] - lo;
     used = k + 1;
     Seg seg[8];
     int cnt = in(lo, m, seg);
@@ -1230,8 +1251,8 @@ static int run_chunked(Ctx& c, size_t n, int chunks, size_t per, unsigned launch
     CK(cudaEventRecord(c.ev_done[k], ks));
   }
   for (int k = 0; k < used; k++) {
-    size_t lo = (size_t)k * per;
-    size_t m = (lo + per <= n) ? per : n - lo;
+    size_t lo = P.lo[k];
+    size_t m = P.lo[k + 1] - lo;
     CK(cudaStreamWaitEvent(cs, c.ev_done[k], 0));
     Seg seg[8];
     int cnt = out(lo, m, seg);
@@ -1730,8 +1751,9 @@ static int eddsa_on(Ctx& c, size_t n, const uint8_t* R, const uint8_t* S, const 
                     const uint8_t* msgs, const uint64_t* msg_off, uint8_t* status) {
   int rc = ensure_table(c, EB200_CURVE_ED25519);
   if (rc) return rc;
-  int chunks; size_t per;
-  plan_chunks(n, &chunks, &per);
+  const ChunkPlan P = make_plan(n);
+  const int chunks = P.chunks;
+  const size_t per = P.max_m;
   size_t mbytes = h ? 0 : (size_t)(msg_off[n] - msg_off[0]);
   size_t off_bytes = h ? 0 : (n + 1) * sizeof(uint64_t);
   size_t base = align256(n * 128);
@@ -1743,7 +1765,7 @@ static int eddsa_on(Ctx& c, size_t n, const uint8_t* R, const uint8_t* S, const 
   uint64_t* doff = (uint64_t*)(c.d_in + base);
   uint8_t* dm = c.d_in + base + align256(off_bytes);
   const u32* gt = c.gtab[EB200_CURVE_ED25519];
-  return run_chunked(c, n, chunks, per, h ? 1u : 2u,
+  return run_chunked(c, P, h ? 1u : 2u,
     [&](size_t lo, size_t m, Seg* seg) {
       seg[0] = {dR + 32 * lo, R + 32 * lo, 32 * m};
       seg[1] = {dS + 32 * lo, S + 32 * lo, 32 * m};
@@ -1799,12 +1821,11 @@ static int eddsa_sign_on(Ctx& c, size_t n, const uint8_t* secrets, const uint8_t
 
 static int x25519_on(Ctx& c, size_t n, const uint8_t* priv, const uint8_t* pubx, uint8_t* out, uint8_t* status, bool validate) {
   int rc;
-  int chunks; size_t per;
-  plan_chunks(n, &chunks, &per);
+  const ChunkPlan P = make_plan(n);
   if ((rc = grow(&c.d_in, &c.d_in_cap, n * 96))) return rc;
   if ((rc = grow(&c.d_status, &c.d_status_cap, n))) return rc;
   uint8_t *dk = c.d_in, *dx = dk + 32 * n, *dout = dx + 32 * n;
-  return run_chunked(c, n, chunks, per, 1u,
+  return run_chunked(c, P, 1u,
     [&](size_t lo, size_t m, Seg* seg) {
       seg[0] = {dk + 32 * lo, priv + 32 * lo, 32 * m};
       seg[1] = {dx + 32 * lo, pubx + 32 * lo, 32 * m};

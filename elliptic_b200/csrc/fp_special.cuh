@@ -21,6 +21,13 @@ namespace eb {
 #include "sqr_gen.inc"
 #endif
 
+// EB_SOLINAS_COLUMNS=1 (default): the p256 / p384 reductions read the standard's word vectors down their columns
+// (tools/gen_solinas.py -> solinas_gen.inc); 0: the vector-wise carry chains below (round-2 first version).
+#ifndef EB_SOLINAS_COLUMNS
+#define EB_SOLINAS_COLUMNS 1
+#endif
+#include "solinas_gen.inc"
+
 // acc (N words) += / -= v, returns the carry / borrow
 template <int N> EB_HD int sp_addv(u32* acc, const u32* v) { return (int)add_n<N>(acc, acc, v); }
 template <int N> EB_HD int sp_subv(u32* acc, const u32* v) { return (int)sub_n<N>(acc, acc, v); }
@@ -58,6 +65,12 @@ template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32
 struct RedP256 {
   static constexpr int N = 8, WN = 8;
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
+#if EB_SOLINAS_COLUMNS
+    u32 v[8];
+    solinas_p256(v, c);
+    sp_final<8>(r, v, 0, p);
+    return;
+#endif
     // value = acc + top * 2^256, top in [-4, 5].  2^256 = K (mod p), K = 2^224 - 2^192 - 2^96 + 1:
     // acc + (top + 4) K + (-4 K mod p), all terms non-negative; C4 = -4 K mod p rides along with s1
     const u32 K[8] = {0x00000001u, 0, 0, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfffffffeu, 0};
@@ -89,6 +102,12 @@ struct RedP256 {
 struct RedP384 {
   static constexpr int N = 12, WN = 12;
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
+#if EB_SOLINAS_COLUMNS
+    u32 v[12];
+    solinas_p384(v, c);
+    sp_final<12>(r, v, 0, p);
+    return;
+#endif
     // value = acc + top * 2^384, top in [-3, 7].  2^384 = K (mod p), K = 2^128 + 2^96 - 2^32 + 1; C3 = -3 K mod p
     const u32 K[12] = {0x00000001u, 0xffffffffu, 0xffffffffu, 0, 0x00000001u, 0, 0, 0, 0, 0, 0, 0};
     const u32 C3[12] = {0xfffffffcu, 0x00000003u, 0x00000000u, 0xfffffffcu, 0xfffffffbu, 0xffffffffu,
