@@ -52,6 +52,19 @@ template <int N> EB_HD void sp_final(u32* r, const u32* acc, u32 carry, const u3
   for (int i = 0; i < N; i++) r[i] = ge ? d[i] : acc[i];
 }
 
+// v in [0, 2^(32N)), v < 2p, top limb of p all ones  ->  canonical residue.  v >= p needs v's top limb to be all
+// ones, which a product's residue class hits with probability 2^-32: the comparison and the subtraction sit in a
+// branch that a warp takes (all lanes together) only when one of its lanes is in that sliver.
+template <int N> EB_HD void sp_final_rare(u32* v, const u32* p) {
+  if (v[N - 1] == 0xffffffffu) {
+    u32 d[N];
+    if (!sub_n<N>(d, v, p)) {
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = d[i];
+    }
+  }
+}
+
 // r = a + b + c word-wise with the carries counted (a, b, c: N words); returns the carry count (0..2)
 template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32* c) {
   int t = (int)add_n<N>(r, a, b);
@@ -66,9 +79,8 @@ struct RedP256 {
   static constexpr int N = 8, WN = 8;
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    u32 v[8];
-    solinas_p256(v, c);
-    sp_final<8>(r, v, 0, p);
+    solinas_p256(r, c);
+    sp_final_rare<8>(r, p);
     return;
 #endif
     // value = acc + top * 2^256, top in [-4, 5].  2^256 = K (mod p), K = 2^224 - 2^192 - 2^96 + 1:
@@ -103,9 +115,8 @@ struct RedP384 {
   static constexpr int N = 12, WN = 12;
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    u32 v[12];
-    solinas_p384(v, c);
-    sp_final<12>(r, v, 0, p);
+    solinas_p384(r, c);
+    sp_final_rare<12>(r, p);
     return;
 #endif
     // value = acc + top * 2^384, top in [-3, 7].  2^384 = K (mod p), K = 2^128 + 2^96 - 2^32 + 1; C3 = -3 K mod p
@@ -151,13 +162,18 @@ struct RedP521 {
 #pragma unroll
     for (int i = 0; i < 17; i++) one[i] = i == 0 ? k : 0u;
     add_n<17>(lo, lo, one);                      // <= 2^521 - 1 (see the derivation in DESIGN.md: the sum was <= 2^522 - 2)
-    u32 all = lo[16] ^ 0x1ffu;
 #pragma unroll
-    for (int i = 0; i < 16; i++) all |= ~lo[i];
-    bool is_p = all == 0;
-#pragma unroll
-    for (int i = 0; i < 17; i++) r[i] = is_p ? 0u : lo[i];
+    for (int i = 0; i < 17; i++) r[i] = lo[i];
     r[17] = 0;
+    if (lo[15] == 0xffffffffu) {                 // lo == p (all 521 bits set) -> 0; one word screens it out (2^-32)
+      u32 all = lo[16] ^ 0x1ffu;
+#pragma unroll
+      for (int i = 0; i < 16; i++) all |= ~lo[i];
+      if (all == 0) {
+#pragma unroll
+        for (int i = 0; i < 17; i++) r[i] = 0;
+      }
+    }
   }
 };
 

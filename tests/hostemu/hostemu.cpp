@@ -459,6 +459,11 @@ static void sw_fe_op_t(int op, const u32* a, const u32* b, u32* out) {
   }
   store_fe_n<NL>(out, F::from_mont(R));
 }
+// the word-level reduction alone: c = lo + hi 2^(32 NL) (any words) -> canonical residue
+extern "C" void he_solinas_reduce(int curve, const u32* c, u32* out) {
+  if (curve == 2) { u32 t[18], p[8]; for (int i = 0; i < 18; i++) t[i] = i < 16 ? c[i] : 0; P256_FP::mod(p); RedP256::reduce(out, t, p); }
+  else { u32 t[26], p[12]; for (int i = 0; i < 26; i++) t[i] = i < 24 ? c[i] : 0; P384_FP::mod(p); RedP384::reduce(out, t, p); }
+}
 extern "C" void he_sw_fe_op(int curve, int op, const u32* a, const u32* b, u32* out) {
   switch (curve) {
     case 2: sw_fe_op_t<P256>(op, a, b, out); break;

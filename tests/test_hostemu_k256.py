@@ -3,6 +3,7 @@ C++ fallbacks of the .cuh headers on the CPU (tests/hostemu) and compared with t
 The PTX paths themselves are covered by the -m gpu tests."""
 import ctypes
 import os
+import sys
 import random
 import subprocess
 
@@ -568,6 +569,53 @@ def test_sw_coordinate_field_ops(he, cid, nl, p):
         assert op(4, a) == -a % p and op(6, a) == a % p
     for a in vals[:10]:
         assert op(7, a) == pow(a % p, p - 2, p)
+
+
+@pytest.mark.parametrize("cid,name", [(2, "P256"), (3, "P384")])
+def test_solinas_reduction_rare_branches(he, cid, name):
+    """The column-wise reductions (tools/gen_solinas.py) keep two steps in branches that random products almost never
+    take: the second fold (the first fold wrapped 2^(32N), in either direction) and the final subtraction (result's top
+    limb all ones).  Inputs are built with the generator's integer model to land in each of them and checked against
+    integer arithmetic; the model also counts how often each branch was really taken."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_solinas as g
+    cfg = getattr(g, name)
+    nl = cfg["N"]
+    p = {"P256": 2**256 - 2**224 + 2**192 + 2**96 - 1, "P384": 2**384 - 2**128 - 2**96 + 2**32 - 1}[name]
+    R = 2**(32 * nl)
+    K = sum(d << (32 * j) for j, d in cfg["K"].items())
+    cols = g.columns(cfg)
+    rnd = random.Random(7 + cid)
+
+    def model(c):                      # (top, top2) of the generated code's two folds
+        tot = sum(coef * c[i] << (32 * j) for j, col in enumerate(cols) for i, coef in col.items())
+        top, w = tot >> (32 * nl), tot & (R - 1)
+        return top, (w + top * K) >> (32 * nl)
+
+    cases = []
+    for _ in range(400):
+        hi = [rnd.choice([0, 0xFFFFFFFF, rnd.randrange(2**32)]) for _ in range(nl)]
+        F = sum(coef * hi[i - nl] << (32 * j) for j, col in enumerate(cols) for i, coef in col.items() if i >= nl)
+        for w in (rnd.randrange(3 * K), R - 1 - rnd.randrange(3 * K), rnd.randrange(K), R - 1 - rnd.randrange(K), p + rnd.randrange(-4, 4) if True else 0):
+            lo = (w - F) % R           # the low half enters every column with coefficient 1: w = (lo + F) mod R
+            cases.append([(lo >> (32 * i)) & 0xFFFFFFFF for i in range(nl)] + hi)
+    for v in (0, R - 1, R * R - 1, (p - 1) ** 2, p * p - 1, (R - 1) * R, R, p, p - 1, R + p, (R - 1) * (R - 1)):
+        cases.append([(v >> (32 * i)) & 0xFFFFFFFF for i in range(2 * nl)])
+    cases += [[rnd.randrange(2**32) for _ in range(2 * nl)] for _ in range(300)]
+    seen = {-1: 0, 0: 0, 1: 0}
+    hit_top = 0
+    for c in cases:
+        v = sum(x << (32 * i) for i, x in enumerate(c))
+        out = (ctypes.c_uint32 * nl)()
+        he.he_solinas_reduce(cid, (ctypes.c_uint32 * (2 * nl))(*c), out)
+        got = I(out, nl)
+        assert got == v % p, hex(v)
+        seen[model(c)[1]] += 1
+        hit_top += got >> (32 * (nl - 1)) == 0xFFFFFFFF
+    # p384: the word sums leave the top in [-1, 3] and a negative top cannot coincide with a low part below K, so
+    # the downward wrap exists only for p256 (top in [-4, 4])
+    assert seen[1] > 50 and seen[0] > 300 and (seen[-1] > 50 if name == "P256" else seen[-1] == 0), seen
+    assert hit_top > 20            # the final-subtraction branch was exercised (and not taken blindly)
 
 
 def test_eddsa_sign_body_reproduces_sign_input(he):
