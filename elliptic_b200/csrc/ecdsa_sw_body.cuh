@@ -49,14 +49,12 @@ struct SW {
   static EB_HD jac dbl_inl(const jac& p) {
     fe delta = F::sqr(p.z);
     fe gamma = F::sqr(p.y);
-    fe beta = F::mul(p.x, gamma);
-    fe alpha = F::mul(F::sub(p.x, delta), F::add(p.x, delta));
-    alpha = F::add(F::dbl(alpha), alpha);
-    fe beta4 = F::dbl(F::dbl(beta));
+    fe beta4 = F::template mul_k<4>(p.x, gamma);                                    // 4 x y^2
+    fe alpha = F::template mul_k<3>(F::sub(p.x, delta), F::add(p.x, delta));        // 3 (x - z^2)(x + z^2)
     jac r;
     r.x = F::sub(F::sqr(alpha), F::dbl(beta4));
     r.z = F::sub(F::sub(F::sqr(F::add(p.y, p.z)), gamma), delta);
-    fe g8 = F::dbl(F::dbl(F::dbl(F::sqr(gamma))));
+    fe g8 = F::template sqr_k<8>(gamma);                                            // 8 y^4
     r.y = F::sub(F::mul(alpha, F::sub(beta4, r.x)), g8);
     return r;
   }

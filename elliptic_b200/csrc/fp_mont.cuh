@@ -175,6 +175,17 @@ struct Fp {
     return r;
   }
   static EB_HD fe sqr(const fe& a) { return mul(a, a); }
+  // K a b and K a^2 for the small constants of the doubling formulas (K = 3, 4, 8): here by modular doublings of the
+  // product; FpS (fp_special.cuh) folds K into the reduction instead
+  template <int K> static EB_HD fe scale_k(const fe& r) {
+    static_assert(K == 1 || K == 3 || K == 4 || K == 8, "scale");
+    if (K == 3) return add(add(r, r), r);
+    if (K == 4) { fe t = add(r, r); return add(t, t); }
+    if (K == 8) { fe t = add(r, r); t = add(t, t); return add(t, t); }
+    return r;
+  }
+  template <int K> static EB_HD fe mul_k(const fe& a, const fe& b) { return scale_k<K>(mul(a, b)); }
+  template <int K> static EB_HD fe sqr_k(const fe& a) { return scale_k<K>(sqr(a)); }
 
 #if defined(__CUDA_ARCH__)
   // Device add / sub for moduli whose top limb is 0xFFFFFFFF (p256, p384 and their group orders): a carry out of

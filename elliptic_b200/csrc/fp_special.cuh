@@ -77,10 +77,14 @@ template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32
 // with two warps per scheduler that latency, not the instruction count, sets the pace.
 struct RedP256 {
   static constexpr int N = 8, WN = 8;
+  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0;      // reduce_scaled<K> exists
+  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) {
+    solinas_p256(r, c, K);
+    sp_final_rare<8>(r, p);
+  }
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    solinas_p256(r, c);
-    sp_final_rare<8>(r, p);
+    reduce_scaled<1>(r, c, p);
     return;
 #endif
     // value = acc + top * 2^256, top in [-4, 5].  2^256 = K (mod p), K = 2^224 - 2^192 - 2^96 + 1:
@@ -113,10 +117,14 @@ struct RedP256 {
 // ---- p384: r = s1 + 2 s2 + s3 + s4 + s5 + s6 + s7 - s8 - s9 - s10  (FIPS 186-4 D.2.4) ----------------------
 struct RedP384 {
   static constexpr int N = 12, WN = 12;
+  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0;
+  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) {
+    solinas_p384(r, c, K);
+    sp_final_rare<12>(r, p);
+  }
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    solinas_p384(r, c);
-    sp_final_rare<12>(r, p);
+    reduce_scaled<1>(r, c, p);
     return;
 #endif
     // value = acc + top * 2^384, top in [-3, 7].  2^384 = K (mod p), K = 2^128 + 2^96 - 2^32 + 1; C3 = -3 K mod p
@@ -147,6 +155,8 @@ struct RedP384 {
 // ---- p521 = 2^521 - 1 in an 18-word container (521 bits = 16 words + 9 bits; word 17 is always 0) -------------
 struct RedP521 {
   static constexpr int N = 18, WN = 17;
+  static constexpr bool SCALED = false;
+  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) { reduce(r, c, p); }   // never used
   static EB_HD void reduce(u32* r, const u32* c, const u32* /*p*/) {
     // c < 2^1042 (36 words, the top ones zero): (c mod 2^521) + (c >> 521), twice, then p -> 0
     u32 lo[17], hi[17];
@@ -187,18 +197,11 @@ struct FpS {
   static EB_HD fe zero() { fe r; for (int i = 0; i < N; i++) r.v[i] = 0; return r; }
   static EB_HD fe one() { fe r = zero(); r.v[0] = 1; return r; }
 
-  static EB_HD fe mul_inl(const fe& a, const fe& b) {
-    u32 t[2 * N + 2], p[N];
-    P::mod(p);
+  static EB_HD void wide_mul(u32* t, const fe& a, const fe& b) {
     mul_wide<N>(t, a.v, b.v);
     t[2 * N] = 0; t[2 * N + 1] = 0;
-    fe r;
-    RED::reduce(r.v, t, p);
-    return r;
   }
-  static EB_HD fe sqr_inl(const fe& a) {
-    u32 t[2 * N + 2], p[N];
-    P::mod(p);
+  static EB_HD void wide_sqr(u32* t, const fe& a) {
 #if defined(__CUDA_ARCH__) && !defined(EB_SQR_AS_MUL)
     if (RED::WN == 8) sqr_wide8_ptx(t, a.v);
     else if (RED::WN == 12) sqr_wide12_ptx(t, a.v);
@@ -207,14 +210,63 @@ struct FpS {
     mul_wide<N>(t, a.v, a.v);
 #endif
     t[2 * N] = 0; t[2 * N + 1] = 0;
+  }
+  static EB_HD fe mul_inl(const fe& a, const fe& b) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+    wide_mul(t, a, b);
     fe r;
     RED::reduce(r.v, t, p);
+    return r;
+  }
+  static EB_HD fe sqr_inl(const fe& a) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+    wide_sqr(t, a);
+    fe r;
+    RED::reduce(r.v, t, p);
+    return r;
+  }
+  // K a b / K a^2, K in {3, 4, 8}: the factor rides through the column sums of the reduction (RED::SCALED) instead of
+  // two or three modular doublings of the result
+  template <int K> static EB_HD fe mulk_inl(const fe& a, const fe& b) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+    wide_mul(t, a, b);
+    fe r;
+    RED::template reduce_scaled<K>(r.v, t, p);
+    return r;
+  }
+  template <int K> static EB_HD fe sqrk_inl(const fe& a) {
+    u32 t[2 * N + 2], p[N];
+    P::mod(p);
+    wide_sqr(t, a);
+    fe r;
+    RED::template reduce_scaled<K>(r.v, t, p);
     return r;
   }
 #if defined(__CUDACC__)
   static __device__ __noinline__ fe mul_ol(fe a, fe b) { return mul_inl(a, b); }
   static __device__ __noinline__ fe sqr_ol(fe a) { return sqr_inl(a); }
+  template <int K> static __device__ __noinline__ fe mulk_ol(fe a, fe b) { return mulk_inl<K>(a, b); }
+  template <int K> static __device__ __noinline__ fe sqrk_ol(fe a) { return sqrk_inl<K>(a); }
 #endif
+  template <int K> static EB_HD fe mul_k(const fe& a, const fe& b) {
+    if (!RED::SCALED) return G::template scale_k<K>(mul(a, b));
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
+    return mulk_ol<K>(a, b);
+#else
+    return mulk_inl<K>(a, b);
+#endif
+  }
+  template <int K> static EB_HD fe sqr_k(const fe& a) {
+    if (!RED::SCALED) return G::template scale_k<K>(sqr(a));
+#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
+    return sqrk_ol<K>(a);
+#else
+    return sqrk_inl<K>(a);
+#endif
+  }
   static EB_HD fe mul(const fe& a, const fe& b) {
 #if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
     return mul_ol(a, b);

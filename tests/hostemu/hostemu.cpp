@@ -455,14 +455,27 @@ static void sw_fe_op_t(int op, const u32* a, const u32* b, u32* out) {
     case 3: R = F::sub(A, B); break;
     case 4: R = F::neg(A); break;
     case 7: R = F::inv(A); break;
+    case 8: R = F::template mul_k<3>(A, B); break;
+    case 9: R = F::template mul_k<4>(A, B); break;
+    case 10: R = F::template sqr_k<8>(A); break;
     default: R = A;
   }
   store_fe_n<NL>(out, F::from_mont(R));
 }
 // the word-level reduction alone: c = lo + hi 2^(32 NL) (any words) -> canonical residue
-extern "C" void he_solinas_reduce(int curve, const u32* c, u32* out) {
-  if (curve == 2) { u32 t[18], p[8]; for (int i = 0; i < 18; i++) t[i] = i < 16 ? c[i] : 0; P256_FP::mod(p); RedP256::reduce(out, t, p); }
-  else { u32 t[26], p[12]; for (int i = 0; i < 26; i++) t[i] = i < 24 ? c[i] : 0; P384_FP::mod(p); RedP384::reduce(out, t, p); }
+template <class RED, class PF, int NL>
+static void solinas_reduce_t(const u32* c, int scale, u32* out) {
+  u32 t[2 * NL + 2], p[NL];
+  for (int i = 0; i < 2 * NL + 2; i++) t[i] = i < 2 * NL ? c[i] : 0;
+  PF::mod(p);
+  if (scale == 3) RED::template reduce_scaled<3>(out, t, p);
+  else if (scale == 4) RED::template reduce_scaled<4>(out, t, p);
+  else if (scale == 8) RED::template reduce_scaled<8>(out, t, p);
+  else RED::reduce(out, t, p);
+}
+extern "C" void he_solinas_reduce(int curve, const u32* c, int scale, u32* out) {
+  if (curve == 2) solinas_reduce_t<RedP256, P256_FP, 8>(c, scale, out);
+  else solinas_reduce_t<RedP384, P384_FP, 12>(c, scale, out);
 }
 extern "C" void he_sw_fe_op(int curve, int op, const u32* a, const u32* b, u32* out) {
   switch (curve) {

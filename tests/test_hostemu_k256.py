@@ -566,6 +566,9 @@ def test_sw_coordinate_field_ops(he, cid, nl, p):
             assert op(2, a, b) == (a + b) % p
             assert op(3, a, b) == (a - b) % p
         assert op(1, a) == a * a % p, hex(a)
+        assert op(10, a) == 8 * a * a % p, hex(a)
+        for b in vals[:6]:
+            assert op(8, a, b) == 3 * a * b % p and op(9, a, b) == 4 * a * b % p, (hex(a), hex(b))
         assert op(4, a) == -a % p and op(6, a) == a % p
     for a in vals[:10]:
         assert op(7, a) == pow(a % p, p - 2, p)
@@ -607,11 +610,18 @@ def test_solinas_reduction_rare_branches(he, cid, name):
     for c in cases:
         v = sum(x << (32 * i) for i, x in enumerate(c))
         out = (ctypes.c_uint32 * nl)()
-        he.he_solinas_reduce(cid, (ctypes.c_uint32 * (2 * nl))(*c), out)
+        he.he_solinas_reduce(cid, (ctypes.c_uint32 * (2 * nl))(*c), 1, out)
         got = I(out, nl)
         assert got == v % p, hex(v)
         seen[model(c)[1]] += 1
         hit_top += got >> (32 * (nl - 1)) == 0xFFFFFFFF
+    # the scaled forms (3 a b, 4 a b, 8 a^2 of the doubling): same inputs, the factor applied inside the column sums
+    for k in (3, 4, 8):
+        for c in cases[::3]:
+            v = sum(x << (32 * i) for i, x in enumerate(c))
+            out = (ctypes.c_uint32 * nl)()
+            he.he_solinas_reduce(cid, (ctypes.c_uint32 * (2 * nl))(*c), k, out)
+            assert I(out, nl) == k * v % p, (k, hex(v))
     # p384: the word sums leave the top in [-1, 3] and a negative top cannot coincide with a low part below K, so
     # the downward wrap exists only for p256 (top in [-4, 4])
     assert seen[1] > 50 and seen[0] > 300 and (seen[-1] > 50 if name == "P256" else seen[-1] == 0), seen

@@ -6,6 +6,9 @@ word that leaves the top is folded back twice with 2^(32N) = K (mod p), K given 
 vector-wise form (nine / ten N-word carry chains joined at the end) this needs no carry bookkeeping: 110 instead of
 150 instructions per p256 reduction on sm_100a.
 
+A small scale factor (1, 3, 4, 8: the constants of the a = -3 doubling) can be applied to the value on the way: the
+column sums have the headroom, and the top word grows to at most +-32, still far from wrapping twice.
+
 Range argument (checked by tests/test_hostemu_k256.py on edge operands): value = w + top 2^(32N), w in [0, 2^(32N)),
 top in [-4, 4] (p256) / [-1, 3] (p384; exact, from the column polynomials); V2 = w + top K lies in (-p, 2p), so its own top word t2 is -1, 0 or 1; V3 = low(V2)
 + t2 K lies in [0, 2^(32N)) with no carry or borrow (t2 = -1 means low(V2) >= 2^(32N) - 6 K; t2 = +1 means low(V2) <
@@ -81,12 +84,14 @@ def gen(cfg):
     N, name = cfg["N"], cfg["name"]
     L = ["// v[%d] = the double-width value c[%d] folded to [0, 2^%d), congruent mod %s (one conditional subtraction left)"
          % (N, 2 * N, 32 * N, name),
-         "EB_HD void solinas_%s(u32* v, const u32* c) {" % name,
+         "// scale (1, 3, 4 or 8; a compile-time constant at every call site) multiplies the value first: k a b costs one",
+         "// 64-bit multiply per column here instead of two or three modular doublings of the reduced product",
+         "EB_HD void solinas_%s(u32* v, const u32* c, const int scale = 1) {" % name,
          "  typedef long long s64;"]
     cols = columns(cfg)
     prev = None
     for j, coef in enumerate(cols):
-        e = expr(coef)
+        e = "scale * (%s)" % expr(coef)
         if prev:
             e += " + (%s >> 32)" % prev
         L.append("  const s64 t%d = %s;" % (j, e))
@@ -123,11 +128,12 @@ def main():
     for cfg, p in ((P256, 2**256 - 2**224 + 2**192 + 2**96 - 1), (P384, 2**384 - 2**128 - 2**96 + 2**32 - 1)):
         N = cfg["N"]
         rnd = random.Random(1)
-        for _ in range(2000):
+        for it in range(4000):
+            scale = (1, 3, 4, 8)[it % 4]
             val = rnd.randrange(p * p) if rnd.random() < 0.8 else (p - 1) ** 2 - rnd.randrange(3)
             c = [(val >> (32 * i)) & 0xffffffff for i in range(2 * N)]
-            tot = sum(coef * c[i] << (32 * j) for j, col in enumerate(columns(cfg)) for i, coef in col.items())
-            assert tot % p == val % p, cfg["name"]
+            tot = scale * sum(coef * c[i] << (32 * j) for j, col in enumerate(columns(cfg)) for i, coef in col.items())
+            assert tot % p == scale * val % p, cfg["name"]
             top = tot >> (32 * N)
             w = tot & ((1 << 32 * N) - 1)
             Kint = sum(d << (32 * j) for j, d in cfg["K"].items())
@@ -136,7 +142,9 @@ def main():
             t2 = v2 >> (32 * N)
             assert t2 in (-1, 0, 1), (cfg["name"], top, t2)
             v3 = (v2 & ((1 << 32 * N) - 1)) + t2 * Kint
-            assert 0 <= v3 < (1 << 32 * N) and v3 < 2 * p and v3 % p == val % p
+            assert 0 <= v3 < (1 << 32 * N) and v3 < 2 * p and v3 % p == scale * val % p
+        # worst cases of the scaled top word: |top| <= 8 * 4 (p256), so |top| K < 2^(32N - 27): the folds cannot wrap twice
+        assert 8 * 5 * Kint < (1 << (32 * N - 20))
     print(path)
 
 
