@@ -240,11 +240,14 @@ __global__ void __launch_bounds__(128) sw_prep_kernel(size_t N, const uint8_t* _
   size_t T = (size_t)gridDim.x * blockDim.x;
   SW<C>::prep_thread(tid, T, N, e, r, s, ws, scratch);
 }
+#ifndef EB_SW_MINBLOCKS_BIG
+#define EB_SW_MINBLOCKS_BIG 2     // 12- and 18-limb curves (p384, p521): 255 registers
+#endif
 #ifndef EB_SW_MINBLOCKS8
 #define EB_SW_MINBLOCKS8 4        // 8-limb curves (p256, p224): four 128-thread blocks per SM (128 registers, 224 B of
 #endif                            // spill): 51.1 ms against 52.2 ms with three blocks / 168 registers at N = 2^20 (r02)
 template <class C>
-__global__ void __launch_bounds__(128, (C::N <= 8) ? EB_SW_MINBLOCKS8 : 2)
+__global__ void __launch_bounds__(128, (C::N <= 8) ? EB_SW_MINBLOCKS8 : EB_SW_MINBLOCKS_BIG)
 sw_verify_kernel(size_t N, const uint8_t* __restrict__ pub, const uint8_t* __restrict__ r, const u32* __restrict__ ws,
                  const u32* __restrict__ gtab, u32* __restrict__ qtab, const uint8_t* __restrict__ pre,
                  uint8_t* __restrict__ status) {

@@ -23,6 +23,12 @@ namespace eb {
 
 // EB_SOLINAS_COLUMNS=1 (default): the p256 / p384 reductions read the standard's word vectors down their columns
 // (tools/gen_solinas.py -> solinas_gen.inc); 0: the vector-wise carry chains below (round-2 first version).
+// EB_SOLINAS_SCALED=1: the doubling's constants (3, 4, 8) are applied inside the reduction (F::mul_k / sqr_k through one
+// extra out-of-line body).  Measured in round 2 and left off: p256 43.9 vs 44.0 ms, p384 143.3 vs 139.8 ms -- the extra
+// body costs the instruction cache what the saved modular doublings gain.
+#ifndef EB_SOLINAS_SCALED
+#define EB_SOLINAS_SCALED 0
+#endif
 #ifndef EB_SOLINAS_COLUMNS
 #define EB_SOLINAS_COLUMNS 1
 #endif
@@ -77,14 +83,14 @@ template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32
 // with two warps per scheduler that latency, not the instruction count, sets the pace.
 struct RedP256 {
   static constexpr int N = 8, WN = 8;
-  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0;      // reduce_scaled<K> exists
-  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) {
-    solinas_p256(r, c, K);
+  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0 && EB_SOLINAS_SCALED != 0;
+  static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int k) {
+    solinas_p256(r, c, k);
     sp_final_rare<8>(r, p);
   }
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    reduce_scaled<1>(r, c, p);
+    reduce_scaled(r, c, p, 1);
     return;
 #endif
     // value = acc + top * 2^256, top in [-4, 5].  2^256 = K (mod p), K = 2^224 - 2^192 - 2^96 + 1:
@@ -117,14 +123,14 @@ struct RedP256 {
 // ---- p384: r = s1 + 2 s2 + s3 + s4 + s5 + s6 + s7 - s8 - s9 - s10  (FIPS 186-4 D.2.4) ----------------------
 struct RedP384 {
   static constexpr int N = 12, WN = 12;
-  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0;
-  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) {
-    solinas_p384(r, c, K);
+  static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0 && EB_SOLINAS_SCALED != 0;
+  static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int k) {
+    solinas_p384(r, c, k);
     sp_final_rare<12>(r, p);
   }
   static EB_HD void reduce(u32* r, const u32* c, const u32* p) {
 #if EB_SOLINAS_COLUMNS
-    reduce_scaled<1>(r, c, p);
+    reduce_scaled(r, c, p, 1);
     return;
 #endif
     // value = acc + top * 2^384, top in [-3, 7].  2^384 = K (mod p), K = 2^128 + 2^96 - 2^32 + 1; C3 = -3 K mod p
@@ -156,7 +162,7 @@ struct RedP384 {
 struct RedP521 {
   static constexpr int N = 18, WN = 17;
   static constexpr bool SCALED = false;
-  template <int K> static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p) { reduce(r, c, p); }   // never used
+  static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int) { reduce(r, c, p); }   // never used
   static EB_HD void reduce(u32* r, const u32* c, const u32* /*p*/) {
     // c < 2^1042 (36 words, the top ones zero): (c mod 2^521) + (c >> 521), twice, then p -> 0
     u32 lo[17], hi[17];
@@ -227,45 +233,35 @@ struct FpS {
     RED::reduce(r.v, t, p);
     return r;
   }
-  // K a b / K a^2, K in {3, 4, 8}: the factor rides through the column sums of the reduction (RED::SCALED) instead of
-  // two or three modular doublings of the result
-  template <int K> static EB_HD fe mulk_inl(const fe& a, const fe& b) {
+  // k a b, k in {3, 4, 8} (the constants of the a = -3 doubling): the factor rides through the column sums of the
+  // reduction (RED::SCALED) instead of two or three modular doublings of the result.  ONE out-of-line body with k
+  // as a run-time argument, and k a^2 goes through it as k a a: three specialised bodies (r02: mulk<3>, mulk<4>,
+  // sqrk<8>, +720 instructions) pushed the p256 window loop past the instruction cache (hit rate 99 % -> 88 %,
+  // 44.0 -> 46.5 ms) and lost more than the doublings cost.
+  static EB_HD fe mulk_inl(const fe& a, const fe& b, int k) {
     u32 t[2 * N + 2], p[N];
     P::mod(p);
     wide_mul(t, a, b);
     fe r;
-    RED::template reduce_scaled<K>(r.v, t, p);
-    return r;
-  }
-  template <int K> static EB_HD fe sqrk_inl(const fe& a) {
-    u32 t[2 * N + 2], p[N];
-    P::mod(p);
-    wide_sqr(t, a);
-    fe r;
-    RED::template reduce_scaled<K>(r.v, t, p);
+    RED::reduce_scaled(r.v, t, p, k);
     return r;
   }
 #if defined(__CUDACC__)
   static __device__ __noinline__ fe mul_ol(fe a, fe b) { return mul_inl(a, b); }
   static __device__ __noinline__ fe sqr_ol(fe a) { return sqr_inl(a); }
-  template <int K> static __device__ __noinline__ fe mulk_ol(fe a, fe b) { return mulk_inl<K>(a, b); }
-  template <int K> static __device__ __noinline__ fe sqrk_ol(fe a) { return sqrk_inl<K>(a); }
+  static __device__ __noinline__ fe mulk_ol(fe a, fe b, int k) { return mulk_inl(a, b, k); }
 #endif
   template <int K> static EB_HD fe mul_k(const fe& a, const fe& b) {
     if (!RED::SCALED) return G::template scale_k<K>(mul(a, b));
 #if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
-    return mulk_ol<K>(a, b);
+    return mulk_ol(a, b, K);
 #else
-    return mulk_inl<K>(a, b);
+    return mulk_inl(a, b, K);
 #endif
   }
   template <int K> static EB_HD fe sqr_k(const fe& a) {
     if (!RED::SCALED) return G::template scale_k<K>(sqr(a));
-#if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
-    return sqrk_ol<K>(a);
-#else
-    return sqrk_inl<K>(a);
-#endif
+    return mul_k<K>(a, a);
   }
   static EB_HD fe mul(const fe& a, const fe& b) {
 #if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)

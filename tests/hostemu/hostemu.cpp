@@ -468,9 +468,7 @@ static void solinas_reduce_t(const u32* c, int scale, u32* out) {
   u32 t[2 * NL + 2], p[NL];
   for (int i = 0; i < 2 * NL + 2; i++) t[i] = i < 2 * NL ? c[i] : 0;
   PF::mod(p);
-  if (scale == 3) RED::template reduce_scaled<3>(out, t, p);
-  else if (scale == 4) RED::template reduce_scaled<4>(out, t, p);
-  else if (scale == 8) RED::template reduce_scaled<8>(out, t, p);
+  if (scale != 1) RED::reduce_scaled(out, t, p, scale);
   else RED::reduce(out, t, p);
 }
 extern "C" void he_solinas_reduce(int curve, const u32* c, int scale, u32* out) {
