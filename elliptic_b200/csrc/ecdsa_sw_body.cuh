@@ -185,8 +185,8 @@ struct SW {
       if ((s >> k) & 1) acc = madd(acc, base);
     }
     aff r = to_aff(acc);
-    store_fe_n<N>(out, r.x);
-    store_fe_n<N>(out + N, r.y);
+    store_fe_n<N>(out, F::canon(r.x));       // table entries are stored canonical (and compared as such by the tests)
+    store_fe_n<N>(out + N, F::canon(r.y));
   }
 
   // ---- prep: batched s^-1 (Montgomery trick, BATCH items/thread), u1, u2, odd-ification

@@ -64,8 +64,8 @@ struct SWReplay {
       if ((s >> k) & 1) acc = W::madd(acc, g);
     }
     aff r = W::to_aff(acc);
-    store_fe_n<N>(out, r.x);
-    store_fe_n<N>(out + N, r.y);
+    store_fe_n<N>(out, F::canon(r.x));
+    store_fe_n<N>(out + N, F::canon(r.y));
   }
 
   // Point.jmulAdd(u1, Q, u2) on G, as scheduled by _wnafMulAdd (base.js:128-253)

@@ -184,6 +184,7 @@ struct Fp {
     if (K == 8) { fe t = add(r, r); t = add(t, t); return add(t, t); }
     return r;
   }
+  static EB_HD fe canon(const fe& a) { return a; }          // elements are always canonical here (FpS: see fp_special.cuh)
   template <int K> static EB_HD fe mul_k(const fe& a, const fe& b) { return scale_k<K>(mul(a, b)); }
   template <int K> static EB_HD fe sqr_k(const fe& a) { return scale_k<K>(sqr(a)); }
 

@@ -26,6 +26,13 @@ namespace eb {
 // EB_SOLINAS_SCALED=1: the doubling's constants (3, 4, 8) are applied inside the reduction (F::mul_k / sqr_k through one
 // extra out-of-line body).  Measured in round 2 and left off: p256 43.9 vs 44.0 ms, p384 143.3 vs 139.8 ms -- the extra
 // body costs the instruction cache what the saved modular doublings gain.
+// EB_FPS_WEAK=1 (default): p256 / p384 elements are held WEAKLY reduced -- any representative in [0, 2^(32N)) -- the
+// way fe_k256.cuh holds secp256k1's.  The column reduction accepts any 2N-word input and already ends below 2^(32N),
+// so products need no final subtraction at all; add / sub fold the carry / borrow with 2^(32N) = K (a masked
+// N-word add instead of subtract-compare-select); only is_zero / eq / from_mont look at the value mod p.
+#ifndef EB_FPS_WEAK
+#define EB_FPS_WEAK 1
+#endif
 #ifndef EB_SOLINAS_SCALED
 #define EB_SOLINAS_SCALED 0
 #endif
@@ -84,6 +91,12 @@ template <int N> EB_HD int sp_add3(u32* r, const u32* a, const u32* b, const u32
 struct RedP256 {
   static constexpr int N = 8, WN = 8;
   static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0 && EB_SOLINAS_SCALED != 0;
+  static constexpr bool WEAK = EB_SOLINAS_COLUMNS != 0 && EB_FPS_WEAK != 0;
+  static EB_HD void kwords(u32* k) {           // 2^256 mod p = 2^224 - 2^192 - 2^96 + 1
+    const u32 K[8] = {0x00000001u, 0, 0, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xfffffffeu, 0};
+    for (int i = 0; i < 8; i++) k[i] = K[i];
+  }
+  static EB_HD void reduce_weak(u32* r, const u32* c, int k = 1) { solinas_p256(r, c, k); }   // [0, 2^256), not < p
   static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int k) {
     solinas_p256(r, c, k);
     sp_final_rare<8>(r, p);
@@ -124,6 +137,12 @@ struct RedP256 {
 struct RedP384 {
   static constexpr int N = 12, WN = 12;
   static constexpr bool SCALED = EB_SOLINAS_COLUMNS != 0 && EB_SOLINAS_SCALED != 0;
+  static constexpr bool WEAK = EB_SOLINAS_COLUMNS != 0 && EB_FPS_WEAK != 0;
+  static EB_HD void kwords(u32* k) {           // 2^384 mod p = 2^128 + 2^96 - 2^32 + 1
+    const u32 K[12] = {0x00000001u, 0xffffffffu, 0xffffffffu, 0, 0x00000001u, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 12; i++) k[i] = K[i];
+  }
+  static EB_HD void reduce_weak(u32* r, const u32* c, int k = 1) { solinas_p384(r, c, k); }
   static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int k) {
     solinas_p384(r, c, k);
     sp_final_rare<12>(r, p);
@@ -162,6 +181,9 @@ struct RedP384 {
 struct RedP521 {
   static constexpr int N = 18, WN = 17;
   static constexpr bool SCALED = false;
+  static constexpr bool WEAK = false;
+  static EB_HD void kwords(u32*) {}
+  static EB_HD void reduce_weak(u32* r, const u32* c, int = 1) { reduce(r, c, nullptr); }                 // never used
   static EB_HD void reduce_scaled(u32* r, const u32* c, const u32* p, int) { reduce(r, c, p); }   // never used
   static EB_HD void reduce(u32* r, const u32* c, const u32* /*p*/) {
     // c < 2^1042 (36 words, the top ones zero): (c mod 2^521) + (c >> 521), twice, then p -> 0
@@ -222,7 +244,8 @@ struct FpS {
     P::mod(p);
     wide_mul(t, a, b);
     fe r;
-    RED::reduce(r.v, t, p);
+    if (RED::WEAK) RED::reduce_weak(r.v, t);
+    else RED::reduce(r.v, t, p);
     return r;
   }
   static EB_HD fe sqr_inl(const fe& a) {
@@ -230,7 +253,8 @@ struct FpS {
     P::mod(p);
     wide_sqr(t, a);
     fe r;
-    RED::reduce(r.v, t, p);
+    if (RED::WEAK) RED::reduce_weak(r.v, t);
+    else RED::reduce(r.v, t, p);
     return r;
   }
   // k a b, k in {3, 4, 8} (the constants of the a = -3 doubling): the factor rides through the column sums of the
@@ -243,7 +267,8 @@ struct FpS {
     P::mod(p);
     wide_mul(t, a, b);
     fe r;
-    RED::reduce_scaled(r.v, t, p, k);
+    if (RED::WEAK) RED::reduce_weak(r.v, t, k);
+    else RED::reduce_scaled(r.v, t, p, k);
     return r;
   }
 #if defined(__CUDACC__)
@@ -251,8 +276,15 @@ struct FpS {
   static __device__ __noinline__ fe sqr_ol(fe a) { return sqr_inl(a); }
   static __device__ __noinline__ fe mulk_ol(fe a, fe b, int k) { return mulk_inl(a, b, k); }
 #endif
+  template <int K> static EB_HD fe scale_k(const fe& r) {          // K r by this field's own additions
+    static_assert(K == 1 || K == 3 || K == 4 || K == 8, "scale");
+    if (K == 3) return add(add(r, r), r);
+    if (K == 4) { fe t = add(r, r); return add(t, t); }
+    if (K == 8) { fe t = add(r, r); t = add(t, t); return add(t, t); }
+    return r;
+  }
   template <int K> static EB_HD fe mul_k(const fe& a, const fe& b) {
-    if (!RED::SCALED) return G::template scale_k<K>(mul(a, b));
+    if (!RED::SCALED) return scale_k<K>(mul(a, b));
 #if defined(__CUDA_ARCH__) && !defined(EB_MONT_INLINE)
     return mulk_ol(a, b, K);
 #else
@@ -260,7 +292,7 @@ struct FpS {
 #endif
   }
   template <int K> static EB_HD fe sqr_k(const fe& a) {
-    if (!RED::SCALED) return G::template scale_k<K>(sqr(a));
+    if (!RED::SCALED) return scale_k<K>(sqr(a));
     return mul_k<K>(a, a);
   }
   static EB_HD fe mul(const fe& a, const fe& b) {
@@ -278,12 +310,49 @@ struct FpS {
 #endif
   }
 
-  static EB_HD fe add(const fe& a, const fe& b) { return G::add(a, b); }
-  static EB_HD fe sub(const fe& a, const fe& b) { return G::sub(a, b); }
-  static EB_HD fe neg(const fe& a) { return G::sub(zero(), a); }
-  static EB_HD fe dbl(const fe& a) { return G::add(a, a); }
-  static EB_HD bool is_zero(const fe& a) { return is_zero_n<N>(a.v); }
-  static EB_HD bool eq(const fe& a, const fe& b) { return eq_n<N>(a.v, b.v); }
+  // weak forms: a carry out of a + b is worth K = 2^(32N) mod p, a borrow out of a - b is worth -K.  A second
+  // carry / borrow needs the first result within K of the wrap (2^-32 for p256, 2^-256 for p384): rare branch.
+  static EB_HD fe wadd(const fe& a, const fe& b) {
+    fe r;
+    u32 k[N], km[N];
+    RED::kwords(k);
+    u32 m = 0u - add_n<N>(r.v, a.v, b.v);
+#pragma unroll
+    for (int i = 0; i < N; i++) km[i] = k[i] & m;
+    if (add_n<N>(r.v, r.v, km)) add_n<N>(r.v, r.v, k);
+    return r;
+  }
+  static EB_HD fe wsub(const fe& a, const fe& b) {
+    fe r;
+    u32 k[N], km[N];
+    RED::kwords(k);
+    u32 m = 0u - sub_n<N>(r.v, a.v, b.v);
+#pragma unroll
+    for (int i = 0; i < N; i++) km[i] = k[i] & m;
+    if (sub_n<N>(r.v, r.v, km)) sub_n<N>(r.v, r.v, k);
+    return r;
+  }
+  // the representative in [0, p): only a top limb of all ones can be >= p (both primes' top limbs are all ones)
+  static EB_HD fe canon(const fe& a) {
+    if (!RED::WEAK) return a;
+    fe r = a;
+    u32 p[N];
+    P::mod(p);
+    sp_final_rare<N>(r.v, p);
+    return r;
+  }
+  static EB_HD fe add(const fe& a, const fe& b) { return RED::WEAK ? wadd(a, b) : G::add(a, b); }
+  static EB_HD fe sub(const fe& a, const fe& b) { return RED::WEAK ? wsub(a, b) : G::sub(a, b); }
+  static EB_HD fe neg(const fe& a) { return sub(zero(), a); }
+  static EB_HD fe dbl(const fe& a) { return add(a, a); }
+  static EB_HD bool is_zero(const fe& a) {
+    if (is_zero_n<N>(a.v)) return true;
+    if (!RED::WEAK || a.v[N - 1] != 0xffffffffu) return false;
+    u32 p[N];
+    P::mod(p);
+    return eq_n<N>(a.v, p);                  // 2p > 2^(32N): 0 and p are the only representatives of zero
+  }
+  static EB_HD bool eq(const fe& a, const fe& b) { return RED::WEAK ? is_zero(wsub(a, b)) : eq_n<N>(a.v, b.v); }
   static EB_HD fe cmov(const fe& a, const fe& b, bool c) { return G::cmov(a, b, c); }
 
   // raw integer (< 2^(32N)) -> residue (`toRed`): reduce as a double-width value whose high half is zero
@@ -296,7 +365,7 @@ struct FpS {
     RED::reduce(r.v, t, p);
     return r;
   }
-  static EB_HD fe from_mont(const fe& a) { return a; }
+  static EB_HD fe from_mont(const fe& a) { return canon(a); }
   static EB_HD bool geq_mod(const u32* a) { u32 p[N]; P::mod(p); return geq_n<N>(a, p); }
 
   static EB_HD fe pow(const fe& a, const u32* e) {
