@@ -26,12 +26,14 @@ namespace eb {
 // EB_SOLINAS_SCALED=1: the doubling's constants (3, 4, 8) are applied inside the reduction (F::mul_k / sqr_k through one
 // extra out-of-line body).  Measured in round 2 and left off: p256 43.9 vs 44.0 ms, p384 143.3 vs 139.8 ms -- the extra
 // body costs the instruction cache what the saved modular doublings gain.
-// EB_FPS_WEAK=1 (default): p256 / p384 elements are held WEAKLY reduced -- any representative in [0, 2^(32N)) -- the
-// way fe_k256.cuh holds secp256k1's.  The column reduction accepts any 2N-word input and already ends below 2^(32N),
-// so products need no final subtraction at all; add / sub fold the carry / borrow with 2^(32N) = K (a masked
-// N-word add instead of subtract-compare-select); only is_zero / eq / from_mont look at the value mod p.
+// EB_FPS_WEAK=1: p256 / p384 elements are held WEAKLY reduced -- any representative in [0, 2^(32N)) -- the way
+// fe_k256.cuh holds secp256k1's: products need no final subtraction, add / sub fold the carry / borrow with
+// 2^(32N) = K (a masked N-word add instead of subtract-compare-select), only is_zero / eq / from_mont look at the
+// value mod p.  Bit-exact (host emulation and the GPU suites pass with it) and SLOWER, so off: ptxas predicates the
+// rare second fold of every add / sub instead of branching around it, the group-law bodies grow (p256 dbl 529 ->
+// 615 instructions, add 1038 -> 1365) past the instruction-cache budget: p256 50.4 vs 44.1 ms, p384 141.5 vs 139.5.
 #ifndef EB_FPS_WEAK
-#define EB_FPS_WEAK 1
+#define EB_FPS_WEAK 0
 #endif
 #ifndef EB_SOLINAS_SCALED
 #define EB_SOLINAS_SCALED 0
