@@ -75,7 +75,7 @@ struct SW {
     r.z = F::mul(a.z, h);
     if (F::is_zero(r.z)) {
       if (F::is_zero(a.z)) return from_aff(p);
-      if (F::is_zero(rr)) return dbl_inl(a);
+      if (F::is_zero(rr)) return dbl(a);          // cold: through the out-of-line copy, not another inlined doubling
       return infinity();
     }
     return r;
@@ -101,7 +101,7 @@ struct SW {
     if (F::is_zero(r.z)) {
       if (F::is_zero(a.z)) return b;
       if (F::is_zero(b.z)) return a;
-      if (F::is_zero(rr)) return dbl_inl(a);
+      if (F::is_zero(rr)) return dbl(a);
       return infinity();
     }
     return r;
