@@ -50,6 +50,66 @@ __global__ void k_check(unsigned long long* bad, u32 seed) {
   if (!ok) atomicAdd(bad, 1ull);
 }
 
+// Operands NOT reduced (uniform in [0, R), edges included): which of the two forms still returns something congruent
+// to a + b / a - b?  counts[0] masked != compare-select, [1] compare-select not congruent, [2] masked not congruent
+template <class P>
+__global__ void k_weak(unsigned long long* counts, u32 seed) {
+  typedef Fp<P> F;
+  constexpr int N = F::N;
+  u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+  u32 s = seed + idx * 2654435761u;
+  u32 p[N]; P::mod(p);
+  typename F::fe a, b;
+  for (int k = 0; k < N; k++) {
+    s = s * 1664525u + 1013904223u; a.v[k] = s;
+    s = s * 1664525u + 1013904223u; b.v[k] = s;
+  }
+  if ((idx & 3) == 1) for (int k = N / 2; k < N; k++) a.v[k] = 0xffffffffu;      // a >= p
+  if ((idx & 3) == 2) for (int k = N / 2; k < N; k++) { a.v[k] = 0xffffffffu; b.v[k] = 0xffffffffu; }
+  auto canon = [&](typename F::fe x) { typename F::fe d; for (int t = 0; t < 3; t++) if (!sub_n<N>(d.v, x.v, p)) x = d; return x; };
+  typename F::fe ca = canon(a), cb = canon(b), ra, rs, t;
+  {                                                     // the true residues, from canonical copies
+    u32 cy = add_n<N>(ra.v, ca.v, cb.v);
+    u32 bw = sub_n<N>(t.v, ra.v, p);
+    if (cy || !bw) ra = t;
+    bw = sub_n<N>(rs.v, ca.v, cb.v);
+    add_n<N>(t.v, rs.v, p);
+    if (bw) rs = t;
+  }
+  typename F::fe sa, ss;                                // compare-and-select on the raw operands
+  {
+    u32 cy = add_n<N>(sa.v, a.v, b.v);
+    u32 bw = sub_n<N>(t.v, sa.v, p);
+    if (cy || !bw) sa = t;
+    bw = sub_n<N>(ss.v, a.v, b.v);
+    add_n<N>(t.v, ss.v, p);
+    if (bw) ss = t;
+  }
+  typename F::fe fa = F::add_fast(a, b), fs = F::sub_fast(a, b);
+  bool differ = false, slow_bad = false, fast_bad = false;
+  typename F::fe csa = canon(sa), css = canon(ss), cfa = canon(fa), cfs = canon(fs);
+  for (int k = 0; k < N; k++) {
+    differ = differ || fa.v[k] != sa.v[k] || fs.v[k] != ss.v[k];
+    slow_bad = slow_bad || csa.v[k] != ra.v[k] || css.v[k] != rs.v[k];
+    fast_bad = fast_bad || cfa.v[k] != ra.v[k] || cfs.v[k] != rs.v[k];
+  }
+  if (differ) atomicAdd(counts, 1ull);
+  if (slow_bad) atomicAdd(counts + 1, 1ull);
+  if (fast_bad) atomicAdd(counts + 2, 1ull);
+}
+
+template <class P>
+void run_weak(const char* name, bool first) {
+  u32 pm[Fp<P>::N]; P::mod(pm);
+  if (pm[Fp<P>::N - 1] != 0xffffffffu) return;
+  unsigned long long* d; unsigned long long c[3] = {0, 0, 0};
+  cudaMalloc(&d, 24); cudaMemset(d, 0, 24);
+  k_weak<P><<<4096, 256>>>(d, 424242u);
+  cudaMemcpy(c, d, 24, cudaMemcpyDeviceToHost);
+  printf("%s\"%s\": {\"masked_ne_select\": %llu, \"select_wrong_mod_p\": %llu, \"masked_wrong_mod_p\": %llu}", first ? "" : ", ", name, c[0], c[1], c[2]);
+  cudaFree(d);
+}
+
 template <class P>
 unsigned long long run(const char* name, bool first) {
   u32 pm[Fp<P>::N]; P::mod(pm);
@@ -72,6 +132,8 @@ int main() {
   run<P192_FP>("p192.p", true); run<P224_FP>("p224.p", false);
   run<P192_FN>("p192.n", false); run<P224_FN>("p224.n", false);
   run<P256_FN>("p256.n", false); run<P384_FN>("p384.n", false); run<K256_FN>("secp256k1.n", false);
+  printf("}, \"unreduced_operands_1048576_pairs\": {");
+  run_weak<P192_FP>("p192.p", true); run_weak<P256_FN>("p256.n", false); run_weak<P384_FN>("p384.n", false); run_weak<K256_FN>("secp256k1.n", false);
   printf("}}\n");
   return 0;
 }
