@@ -544,6 +544,10 @@ rt_curve_kernel(int op, size_t N, RtCurve<NL> C, const uint8_t* __restrict__ k1,
 // thread on its own device; device-pointer calls run on the device that owns the pointers.
 namespace {
 constexpr int MAX_CHUNKS = 16;
+}  // namespace
+#define EB_MAX_CHUNKS 16
+#include "chunk_plan.h"
+namespace {
 constexpr int MAX_DEV = 16;
 constexpr int STAGE_SLOTS = 8;                       // pinned staging ring for pageable caller buffers
 constexpr size_t STAGE_BYTES = (size_t)4 << 20;
@@ -1120,42 +1124,7 @@ int eb200_ecdsa_verify_batch_dev(int curve, size_t n, const uint8_t* d_e, const 
 
 // Host-pointer verify on one device.  Large batches are cut into chunks: chunk k+1 is copied host->device on a
 // copy stream while chunk k is being verified, and results stream back as each chunk finishes.
-// Chunk boundaries of a pipelined host call.  Equal chunks, except that the FIRST one is cut short (1/4 of a
-// regular chunk): its host->device copy is the only one no kernel hides, so the shorter it is the sooner the GPU
-// starts (EB200_LEAD=0 restores equal chunks; EB200_CHUNKS overrides the count).
-struct ChunkPlan { int chunks; size_t lo[MAX_CHUNKS + 2]; size_t max_m; };
-static ChunkPlan make_plan(size_t n) {
-  int ch = 1;
-  if (n >= ((size_t)1 << 18)) ch = 4;         // 2^18-item chunks keep the grid tail small (r01: 8 chunks cost 10%)
-  if (n >= ((size_t)1 << 22)) ch = MAX_CHUNKS;
-  if (const char* ev = getenv("EB200_CHUNKS")) { int k = atoi(ev); if (k >= 1 && k <= MAX_CHUNKS) ch = k; }   // tuning knob
-  bool lead = ch > 1 && ch < MAX_CHUNKS;
-  if (const char* ev = getenv("EB200_LEAD")) lead = lead && atoi(ev) != 0;
-  ChunkPlan P;
-  size_t per = (n + ch - 1) / ch;
-  per = (per + 127) & ~(size_t)127;
-  int k = 0;
-  size_t pos = 0;
-  P.lo[0] = 0;
-  if (lead) {
-    size_t first = ((per / 4) + 127) & ~(size_t)127;
-    if (first < n) {
-      pos = first;
-      P.lo[++k] = pos;
-      per = (n - first + ch - 1) / ch;
-      per = (per + 127) & ~(size_t)127;
-    }
-  }
-  while (pos < n) {
-    pos = pos + per < n ? pos + per : n;
-    P.lo[++k] = pos;
-  }
-  P.chunks = k;
-  P.max_m = 0;
-  for (int i = 0; i < k; i++) if (P.lo[i + 1] - P.lo[i] > P.max_m) P.max_m = P.lo[i + 1] - P.lo[i];
-  return P;
-}
-
+// chunk boundaries: chunk_plan.h (make_plan), unit-tested on the CPU through tests/hostemu
 static int verify_on(Ctx& c, int curve, size_t n, const uint8_t* e, const uint8_t* r, const uint8_t* s, const uint8_t* pub,
                      uint32_t pub_fmt, uint8_t* status) {
   int rc = ensure_table(c, curve);

@@ -576,3 +576,13 @@ extern "C" void he_rt_item(int op, const u32* p8, const u32* r1, const u32* r2, 
   C.n0inv = n0inv; C.len = len; C.a_is_zero = 0;
   status[0] = RtG<8>::item(op, 0, k1, p1, k2, p2, klen, out, C);
 }
+
+// ---------------------------------------------------------------------------
+// the chunk plan of the pipelined host calls (pure host logic of the product library)
+#include "../../elliptic_b200/csrc/chunk_plan.h"
+extern "C" int he_chunk_plan(size_t n, unsigned long long* lo /* EB_MAX_CHUNKS + 2 */, unsigned long long* max_m) {
+  ChunkPlan P = make_plan(n);
+  for (int i = 0; i <= P.chunks; i++) lo[i] = P.lo[i];
+  *max_m = P.max_m;
+  return P.chunks;
+}

@@ -893,3 +893,35 @@ def test_runtime_short_curve_bodies(he):
         assert run(prm, ln, 2, S) == aff_add(S, S, pp, aa)
         assert run(prm, ln, 0, P, k1, klen=25) == aff_mul(k1, P, pp, aa)
         assert run(prm, ln, 0, P, k1, Q, k2, klen=25) == aff_add(aff_mul(k1, P, pp, aa), aff_mul(k2, Q, pp, aa), pp, aa)
+
+
+def test_chunk_plan_of_the_pipelined_host_calls(he, monkeypatch):
+    """make_plan (csrc/chunk_plan.h): the chunks tile [0, n) in order, every boundary except the last is a multiple
+    of 128 items (the kernels' block size), there are never more chunks than the context has events for, the lead
+    chunk is the short one, and the tuning knobs do what INTEGRATION.md says."""
+    def plan(n):
+        lo = (ctypes.c_ulonglong * 18)()
+        mx = ctypes.c_ulonglong()
+        k = he.he_chunk_plan(ctypes.c_size_t(n), lo, ctypes.byref(mx))
+        b = [int(lo[i]) for i in range(k + 1)]
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:])), (n, b)
+        assert all(x % 128 == 0 for x in b[:-1]) and 1 <= k <= 16
+        assert int(mx.value) == max(y - x for x, y in zip(b, b[1:]))
+        return b
+    monkeypatch.delenv("EB200_CHUNKS", raising=False)
+    monkeypatch.delenv("EB200_LEAD", raising=False)
+    for n in (1, 127, 128, 129, 4099, (1 << 18) - 1):
+        assert plan(n) == [0, n]                                   # below 2^18 items: one chunk
+    b = plan(1 << 20)
+    assert len(b) == 6 and b[1] == 1 << 16 and max(y - x for x, y in zip(b[1:], b[2:])) <= (1 << 18)   # 1/4 lead + 4
+    assert len(plan(1 << 22)) == 17 and len(plan((1 << 23) + 12345)) == 17                            # 16 equal chunks
+    rnd = random.Random(5)
+    for _ in range(300):
+        plan(rnd.randrange(1, 1 << 24))
+    monkeypatch.setenv("EB200_LEAD", "0")
+    assert plan(1 << 20) == [0, 1 << 18, 2 << 18, 3 << 18, 1 << 20]
+    monkeypatch.setenv("EB200_CHUNKS", "15")
+    monkeypatch.delenv("EB200_LEAD", raising=False)
+    assert len(plan(1 << 20)) == 17                                # 15 + the lead chunk: the most the event arrays hold
+    monkeypatch.setenv("EB200_CHUNKS", "99")                       # out of range: ignored
+    assert len(plan(1 << 20)) == 6
