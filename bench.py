@@ -418,9 +418,10 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # communicator lines (rank count, transport) go to stderr; stdout carries the one JSON line
+        # (no NCCL_DEBUG_FILE: NCCL writes to fd 1, which claim_stdout() has already pointed at stderr; with
+        # NCCL_DEBUG_FILE=/dev/stderr the r02 8-GPU run showed only the version line)
         os.environ.setdefault("NCCL_DEBUG", "INFO")
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = nat.init(local)
     ds = dataset(rank, world)
