@@ -418,10 +418,7 @@ def run_gpu(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # communicator lines (rank count, transport) go to stderr; stdout carries the one JSON line
-        # (no NCCL_DEBUG_FILE: NCCL writes to fd 1, which claim_stdout() has already pointed at stderr; with
-        # NCCL_DEBUG_FILE=/dev/stderr the r02 8-GPU run showed only the version line)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (NCCL's debug level is set in main(), before torch is imported)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     lib = nat.init(local)
     ds = dataset(rank, world)
@@ -677,6 +674,11 @@ def emit(line):
 
 def main():
     claim_stdout()
+    # communicator lines (rank count, transport: NVLS / P2P) are part of the evidence.  Set before anything can load
+    # NCCL; it writes to fd 1, which now is stderr.  The GPU boxes preset VERSION, which hides them: raise that too.
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
