@@ -258,9 +258,11 @@ class EC:
         s = np.ascontiguousarray(s, dtype=np.uint8)
         pub = np.ascontiguousarray(pub, dtype=np.uint8)
         n = e.shape[0]
-        assert e.shape == (n, self._len) and r.shape == e.shape and s.shape == e.shape
+        if not (e.shape == (n, self._len) and r.shape == e.shape and s.shape == e.shape):      # raw pointers go down
+            raise ValueError("e, r, s must be (n, %d) uint8 arrays" % self._len)
         pb = {nat.PUB_XY: 2 * self._len, nat.PUB_SEC1_65: 1 + 2 * self._len, nat.PUB_SEC1_33: 1 + self._len}[pub_fmt]
-        assert pub.shape == (n, pb), (pub.shape, pb)
+        if pub.shape != (n, pb):
+            raise ValueError("pub must be (n, %d) for this format, got %r" % (pb, pub.shape))
         status = np.empty(n, dtype=np.uint8)
         nat.check(lib.eb200_ecdsa_verify_batch(
             self._c["id"], n, e.ctypes.data, r.ctypes.data, s.ctypes.data, pub.ctypes.data,

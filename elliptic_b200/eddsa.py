@@ -41,7 +41,8 @@ class EDDSA:
         lib = nat.init(self._device)
         R, S, A, h = (np.ascontiguousarray(a, dtype=np.uint8) for a in (R, S, A, h))
         n = R.shape[0]
-        assert R.shape == (n, 32) and S.shape == R.shape and A.shape == R.shape and h.shape == R.shape
+        if not (R.shape == (n, 32) and S.shape == R.shape and A.shape == R.shape and h.shape == R.shape):
+            raise ValueError("R, S, A, h must be (n, 32) uint8 arrays")
         status = np.empty(n, np.uint8)
         nat.check(lib.eb200_eddsa_verify_batch(n, R.ctypes.data, S.ctypes.data, A.ctypes.data, h.ctypes.data,
                                                status.ctypes.data))
@@ -55,7 +56,10 @@ class EDDSA:
         msgs = np.ascontiguousarray(msgs, dtype=np.uint8)
         msg_off = np.ascontiguousarray(msg_off, dtype=np.uint64)
         n = R.shape[0]
-        assert msg_off.shape == (n + 1,) and int(msg_off[n]) == msgs.size
+        if not (R.shape == (n, 32) and S.shape == R.shape and A.shape == R.shape):
+            raise ValueError("R, S, A must be (n, 32) uint8 arrays")
+        if not (msg_off.shape == (n + 1,) and int(msg_off[n]) == msgs.size):
+            raise ValueError("msg_off must hold n + 1 offsets, the last one equal to len(msgs)")
         status = np.empty(n, np.uint8)
         nat.check(lib.eb200_eddsa_verify_batch_msgs(n, R.ctypes.data, S.ctypes.data, A.ctypes.data,
                                                     msgs.ctypes.data if msgs.size else None, msg_off.ctypes.data,
